@@ -1,0 +1,138 @@
+"""ctypes binding of libdmel_b200.so — the C ABI declared in include/dmel.h.
+
+There is no CPU fallback: if the shared library is missing or does not export a symbol
+this module raises, and every product entry point goes through it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdmel_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+ABI_VERSION = 1
+FLAG_NORMALIZE_WINDOW = 1
+FLAG_KEEP_MEAN = 2
+
+# every symbol include/dmel.h declares
+EXPORTED_SYMBOLS = (
+    "dmel_abi_version",
+    "dmel_status_string",
+    "dmel_nfft_supported",
+    "dmel_window_length_from_lambda",
+    "dmel_workspace_bytes",
+    "dmel_forward_f32",
+    "dmel_backward_f32",
+    "dmel_query_launch",
+)
+
+
+class MelBankStruct(ctypes.Structure):
+    """struct dmel_melbank (include/dmel.h)."""
+
+    _fields_ = [
+        ("n_freqs", ctypes.c_int32),
+        ("n_mels", ctypes.c_int32),
+        ("mel_k0", ctypes.c_void_p),
+        ("mel_off", ctypes.c_void_p),
+        ("mel_w", ctypes.c_void_p),
+        ("bin_m0", ctypes.c_void_p),
+        ("bin_off", ctypes.c_void_p),
+        ("bin_w", ctypes.c_void_p),
+    ]
+
+
+class DmelError(RuntimeError):
+    pass
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/ for sm_100a into libdmel_b200.so (in-tree) with nvcc."""
+    srcs = [os.path.join(CSRC_DIR, f) for f in ("dmel_kernels.cu", "fft_device.cuh")]
+    srcs.append(os.path.join(_HERE, "..", "include", "dmel.h"))
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(s) for s in srcs if os.path.exists(s))
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    cmd = ["make", "-C", CSRC_DIR] + (["-B"] if force else [])
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or proc.returncode != 0:
+        print(proc.stdout)
+        print(proc.stderr)
+    if proc.returncode != 0:
+        raise DmelError(f"building libdmel_b200.so failed (exit {proc.returncode})")
+    return LIB_PATH
+
+
+def _declare(lib: ctypes.CDLL) -> None:
+    c = ctypes
+    lib.dmel_abi_version.restype = c.c_int
+    lib.dmel_abi_version.argtypes = []
+    lib.dmel_status_string.restype = c.c_char_p
+    lib.dmel_status_string.argtypes = [c.c_int]
+    lib.dmel_nfft_supported.restype = c.c_int
+    lib.dmel_nfft_supported.argtypes = [c.c_int32]
+    lib.dmel_window_length_from_lambda.restype = c.c_int32
+    lib.dmel_window_length_from_lambda.argtypes = [c.c_float]
+    lib.dmel_workspace_bytes.restype = c.c_size_t
+    lib.dmel_workspace_bytes.argtypes = [c.c_int64, c.c_int32]
+    lib.dmel_forward_f32.restype = c.c_int
+    lib.dmel_forward_f32.argtypes = [
+        c.c_void_p, c.c_int64, c.c_int64, c.c_int64,          # x, batch, n_points, stride
+        c.c_float, c.c_int32, c.c_int32, c.c_int32,           # lambda, win_length, n_fft, hop
+        c.c_int32, c.POINTER(MelBankStruct), c.c_float,       # n_mels, bank, log_eps
+        c.c_int32, c.c_void_p,                                # flags, y
+        c.c_void_p, c.c_size_t, c.c_void_p,                   # workspace, bytes, stream
+    ]
+    lib.dmel_backward_f32.restype = c.c_int
+    lib.dmel_backward_f32.argtypes = [
+        c.c_void_p, c.c_int64, c.c_int64, c.c_int64,
+        c.c_float, c.c_int32, c.c_int32, c.c_int32,
+        c.c_int32, c.POINTER(MelBankStruct), c.c_float,
+        c.c_int32, c.c_void_p, c.c_void_p,                    # flags, y, grad_y
+        c.c_void_p, c.c_void_p,                               # grad_x, grad_lambda
+        c.c_void_p, c.c_size_t, c.c_int32, c.c_void_p,        # workspace, bytes, prepared, stream
+    ]
+    lib.dmel_query_launch.restype = c.c_int
+    lib.dmel_query_launch.argtypes = [
+        c.c_int64, c.c_int32, c.c_int32, c.c_int32, c.c_int32,
+        c.POINTER(c.c_int32), c.POINTER(c.c_int32), c.POINTER(c.c_int32), c.POINTER(c.c_int32),
+    ]
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and return the library; raises DmelError if it cannot be used."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise DmelError(
+                f"{LIB_PATH} not found — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C differentiable-mel-spectrogram_b200/csrc`). There is no CPU fallback."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        missing = [s for s in EXPORTED_SYMBOLS if not hasattr(lib, s)]
+        if missing:
+            raise DmelError(f"{LIB_PATH} does not export {missing}")
+        _declare(lib)
+        got = lib.dmel_abi_version()
+        if got != ABI_VERSION:
+            raise DmelError(f"libdmel_b200.so ABI version {got}, binding expects {ABI_VERSION}")
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().dmel_status_string(rc).decode()
+        raise DmelError(f"{what}: {msg} (status {rc})")

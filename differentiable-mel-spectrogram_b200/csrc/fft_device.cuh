@@ -1,0 +1,218 @@
+// fft_device.cuh — in-register / shared-memory complex FFT building blocks (sm_100a).
+//
+// One CTA computes one L-point complex FFT at a time ("packed pair": two real STFT
+// frames ride as the real and imaginary part of one complex transform).  Each of
+// the NT = L/E threads keeps E complex points in registers; a Stockham pass is
+//   load (stride L/R)  ->  twiddle  ->  radix-R DFT in registers  ->  scatter (stride NS)
+// with the scatter/gather going through a ping-pong pair of shared-memory buffers.
+// The shared-memory index is XOR-swizzled per pass so that both the strided scatter
+// of the early passes and the contiguous gather of the next pass are conflict-free
+// for 64-bit accesses (16 lanes x 8 B per wavefront).
+//
+// This replaces the cuFFT/MKL R2C call under torch.stft that the reference reaches
+// from time_frequency.py:48/51 (reference: /root/reference/time_frequency.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dmel {
+
+// ----------------------------------------------------------------------------
+// complex helpers
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+// multiply by -i  (forward-transform quarter turn)
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+// ----------------------------------------------------------------------------
+// radix-R DFT on registers, natural order in / natural order out, sign = -1
+// ----------------------------------------------------------------------------
+template <int R> struct RegDft;
+
+template <> struct RegDft<2> {
+    static __device__ __forceinline__ void run(float2 (&v)[2]) {
+        float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+
+template <> struct RegDft<4> {
+    static __device__ __forceinline__ void run(float2 (&v)[4]) {
+        float2 s02 = cadd(v[0], v[2]), d02 = csub(v[0], v[2]);
+        float2 s13 = cadd(v[1], v[3]), d13 = mul_mi(csub(v[1], v[3]));
+        v[0] = cadd(s02, s13);
+        v[1] = cadd(d02, d13);
+        v[2] = csub(s02, s13);
+        v[3] = csub(d02, d13);
+    }
+};
+
+template <> struct RegDft<8> {
+    static __device__ __forceinline__ void run(float2 (&v)[8]) {
+        constexpr float C = 0.70710678118654752440f;
+        float2 e[4] = {v[0], v[2], v[4], v[6]};
+        float2 o[4] = {v[1], v[3], v[5], v[7]};
+        RegDft<4>::run(e);
+        RegDft<4>::run(o);
+        // o[k] *= exp(-2*pi*i*k/8)
+        float2 o1 = make_float2(C * (o[1].x + o[1].y), C * (o[1].y - o[1].x));
+        float2 o2 = mul_mi(o[2]);
+        float2 o3 = make_float2(C * (o[3].y - o[3].x), -C * (o[3].x + o[3].y));
+        v[0] = cadd(e[0], o[0]);  v[4] = csub(e[0], o[0]);
+        v[1] = cadd(e[1], o1);    v[5] = csub(e[1], o1);
+        v[2] = cadd(e[2], o2);    v[6] = csub(e[2], o2);
+        v[3] = cadd(e[3], o3);    v[7] = csub(e[3], o3);
+    }
+};
+
+template <> struct RegDft<16> {
+    static __device__ __forceinline__ void run(float2 (&v)[16]) {
+        constexpr float C1 = 0.92387953251128675613f;  // cos(pi/8)
+        constexpr float S1 = 0.38268343236508977173f;  // sin(pi/8)
+        constexpr float C2 = 0.70710678118654752440f;  // cos(pi/4)
+        float2 e[8], o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+        RegDft<8>::run(e);
+        RegDft<8>::run(o);
+        // w16^k = (cos(k*pi/8), -sin(k*pi/8))
+        const float2 w[8] = {
+            make_float2(1.f, 0.f),  make_float2(C1, -S1), make_float2(C2, -C2), make_float2(S1, -C1),
+            make_float2(0.f, -1.f), make_float2(-S1, -C1), make_float2(-C2, -C2), make_float2(-C1, -S1)};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float2 t;
+            if (k == 0) t = o[0];
+            else if (k == 4) t = mul_mi(o[4]);
+            else t = cmul(o[k], w[k]);
+            v[k] = cadd(e[k], t);
+            v[k + 8] = csub(e[k], t);
+        }
+    }
+};
+
+// ----------------------------------------------------------------------------
+// FFT plans: E points per thread, NP passes, radices R[p]  (prod R = L)
+// ----------------------------------------------------------------------------
+template <int L> struct Plan;
+template <> struct Plan<128>  { static constexpr int E = 4,  NP = 4, R0 = 4,  R1 = 4,  R2 = 4,  R3 = 2; };
+template <> struct Plan<256>  { static constexpr int E = 8,  NP = 3, R0 = 8,  R1 = 8,  R2 = 4,  R3 = 1; };
+template <> struct Plan<512>  { static constexpr int E = 8,  NP = 3, R0 = 8,  R1 = 8,  R2 = 8,  R3 = 1; };
+template <> struct Plan<1024> { static constexpr int E = 16, NP = 3, R0 = 16, R1 = 8,  R2 = 8,  R3 = 1; };
+template <> struct Plan<2048> { static constexpr int E = 16, NP = 3, R0 = 16, R1 = 16, R2 = 8,  R3 = 1; };
+template <> struct Plan<4096> { static constexpr int E = 16, NP = 3, R0 = 16, R1 = 16, R2 = 16, R3 = 1; };
+template <> struct Plan<8192> { static constexpr int E = 16, NP = 4, R0 = 16, R1 = 8,  R2 = 8,  R3 = 8; };
+
+template <int L, int P> struct PlanRadix;
+template <int L> struct PlanRadix<L, 0> { static constexpr int R = Plan<L>::R0, NS = 1; };
+template <int L> struct PlanRadix<L, 1> { static constexpr int R = Plan<L>::R1, NS = Plan<L>::R0; };
+template <int L> struct PlanRadix<L, 2> { static constexpr int R = Plan<L>::R2, NS = Plan<L>::R0 * Plan<L>::R1; };
+template <int L> struct PlanRadix<L, 3> { static constexpr int R = Plan<L>::R3, NS = Plan<L>::R0 * Plan<L>::R1 * Plan<L>::R2; };
+
+// XOR swizzle of a float2 index inside a 16-entry (128 B) row. `ROT` is chosen per
+// pass (see swz_rot) so that the scatter with stride NS lands on 16 distinct 8-byte
+// bank pairs per half-warp; rows stay rows, so contiguous gathers stay conflict-free.
+template <int ROT> __device__ __forceinline__ int swz(int i) {
+    if (ROT == 0) return i;
+    return i ^ ((ROT * (i >> 4)) & 15);
+}
+__host__ __device__ constexpr int swz_rot(int NS, int R) {
+    return NS >= 16 ? 0 : ((NS * R >= 16) ? (16 / R) : NS);
+}
+
+// ----------------------------------------------------------------------------
+// One Stockham pass, split in its three phases so callers can place barriers.
+//   v[i*R + r]  holds input  j + r*(L/R),  j = tid + i*NT   (after gather)
+//   after compute it holds output index  (j-k)*R + k + r*NS, k = j mod NS
+// ----------------------------------------------------------------------------
+template <int L, int P> struct Pass {
+    static constexpr int E = Plan<L>::E;
+    static constexpr int NT = L / E;
+    static constexpr int R = PlanRadix<L, P>::R;
+    static constexpr int NS = PlanRadix<L, P>::NS;
+    static constexpr int NB = E / R;       // butterflies per thread
+    static constexpr int STR = L / R;      // gather stride
+    static constexpr int ROT_OUT = swz_rot(NS, R);
+    // the layout this pass reads is the one the previous pass wrote
+    static constexpr int ROT_IN = (P == 0) ? 0 : swz_rot(PlanRadix<L, (P > 0 ? P - 1 : 0)>::NS,
+                                                          PlanRadix<L, (P > 0 ? P - 1 : 0)>::R);
+
+    static __device__ __forceinline__ void gather(float2 (&v)[E], const float2* __restrict__ in, int tid) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int j = tid + i * NT;
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[i * R + r] = in[swz<ROT_IN>(j + r * STR)];
+        }
+    }
+
+    // twiddle (table tw[i] = exp(-2*pi*i*idx/L), idx in [0,L)) + radix-R DFT in registers
+    static __device__ __forceinline__ void compute(float2 (&v)[E], const float2* __restrict__ tw, int tid) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int j = tid + i * NT;
+            float2 t[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) t[r] = v[i * R + r];
+            if (NS > 1) {
+                const int k = j & (NS - 1);
+                const int base = k * (L / (NS * R));
+#pragma unroll
+                for (int r = 1; r < R; ++r) t[r] = cmul(t[r], __ldg(&tw[base * r]));
+            }
+            RegDft<R>::run(t);
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[i * R + r] = t[r];
+        }
+    }
+
+    static __device__ __forceinline__ void scatter(const float2 (&v)[E], float2* __restrict__ out, int tid) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int j = tid + i * NT;
+            const int k = j & (NS - 1);
+            const int j0 = (j - k) * R + k;
+#pragma unroll
+            for (int r = 0; r < R; ++r) out[swz<ROT_OUT>(j0 + r * NS)] = v[i * R + r];
+        }
+    }
+
+    // output index held in v[i*R + r] after compute()
+    static __device__ __forceinline__ int out_index(int tid, int i, int r) {
+        const int j = tid + i * NT;
+        const int k = j & (NS - 1);
+        return (j - k) * R + k + r * NS;
+    }
+};
+
+// Runs passes FIRST..NP-1 of the plan.  On entry v holds the gathered inputs of pass
+// FIRST.  Intermediate results ping-pong through buf[sel], buf[sel^1] ...; `sel` is
+// advanced on every scatter so that callers can keep toggling across iterations.
+// If STORE_LAST the natural-order spectrum ends in buf[last written] (linear layout,
+// the last pass always has NS >= 16) and a barrier has been passed; otherwise the last
+// pass leaves its outputs in v (index map Pass<L,NP-1>::out_index) and does not sync.
+template <int L, int P, bool STORE_LAST>
+__device__ __forceinline__ void run_passes(float2 (&v)[Plan<L>::E], float2* buf0, float2* buf1, int& sel,
+                                           const float2* __restrict__ tw, int tid) {
+    Pass<L, P>::compute(v, tw, tid);
+    if constexpr (P + 1 < Plan<L>::NP) {
+        float2* out = sel ? buf1 : buf0;
+        Pass<L, P>::scatter(v, out, tid);
+        sel ^= 1;
+        __syncthreads();
+        Pass<L, P + 1>::gather(v, out, tid);
+        run_passes<L, P + 1, STORE_LAST>(v, buf0, buf1, sel, tw, tid);
+    } else if constexpr (STORE_LAST) {
+        float2* out = sel ? buf1 : buf0;
+        Pass<L, P>::scatter(v, out, tid);
+        sel ^= 1;
+        __syncthreads();
+    }
+}
+
+}  // namespace dmel

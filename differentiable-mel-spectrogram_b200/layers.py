@@ -1,0 +1,100 @@
+"""Drop-in replacements for the reference's differentiable spectrogram layers.
+
+Same constructor arguments, attributes, parameter name (`lambd`, so `spectrogram_layer.lambd`
+keeps matching main.py:39 and state_dicts load, utils.py:269-270), forward signature and
+output contract as
+    models.py:14-56   MelSpectrogramLayer   (B, n_points) -> (B, 1, n_mels, n_points//hop + 1)
+    models.py:171-200 SpectrogramLayer      (B, n_points) -> (B, 1, n_fft/2 + 1, n_points//hop + 1)
+but one fused CUDA forward (and one fused backward) per batch instead of a Python loop of
+~200 ATen calls and two host syncs per sample.  One keyword is appended: `log_eps` fuses the
+`torch.log(s + 1e-10)` every classifier head applies (models.py:72-73); its default (None)
+reproduces the reference's linear output.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .op import dmel
+
+
+def _resolve_device(module_device, lambd: torch.Tensor) -> torch.device:
+    # The reference keeps a `device` attribute and also follows `net.to(device)` (main.py:25).
+    # The parameter's device is the truth once the module has been moved.
+    return lambd.device
+
+
+class MelSpectrogramLayer(nn.Module):
+    def __init__(self, init_lambd, n_mels, n_points, sample_rate, f_min=0, f_max=None, hop_length=1, device='cpu',
+                 optimized=False, normalize_window=False, *, log_eps: Optional[float] = None):
+        super().__init__()
+        self.hop_length = hop_length
+        self.lambd = nn.Parameter(init_lambd)
+        self.device = device
+        self.optimized = optimized
+        self.normalize_window = normalize_window
+
+        self.f_min = f_min
+        self.f_max = f_max if f_max is not None else sample_rate // 2
+        self.n_mels = n_mels
+        self.sample_rate = sample_rate
+
+        self.n_freq = n_mels
+        self.n_time = n_points // hop_length + 1
+        self.log_eps = log_eps
+
+    def forward(self, x):
+        dev = _resolve_device(self.device, self.lambd)
+        if dev.type != 'cuda':
+            raise _lib.DmelError(
+                f"MelSpectrogramLayer lives on {dev}: this implementation is CUDA-only (sm_100a) and has no CPU "
+                "fallback; move the module with .to('cuda') (the reference's default device='cpu' is not served)")
+        if x.device != dev:
+            x = x.to(dev, non_blocking=True)
+        (batch_size, n_points) = x.shape
+        if n_points // self.hop_length + 1 != self.n_time:
+            # the reference fails on the slice assignment models.py:54
+            raise RuntimeError(f"input has {n_points} points -> {n_points // self.hop_length + 1} frames, "
+                               f"layer was built for n_time={self.n_time}")
+        return dmel(x, self.lambd, hop_length=self.hop_length, optimized=self.optimized,
+                    normalize_window=self.normalize_window, n_mels=self.n_mels, sample_rate=self.sample_rate,
+                    f_min=self.f_min, f_max=self.f_max, log_eps=self.log_eps)
+
+    def extra_repr(self):
+        return (f"n_mels={self.n_mels}, sample_rate={self.sample_rate}, hop_length={self.hop_length}, "
+                f"optimized={self.optimized}, normalize_window={self.normalize_window}, log_eps={self.log_eps}")
+
+
+class SpectrogramLayer(nn.Module):
+    def __init__(self, init_lambd, device='cpu', optimized=False, size=(512, 1024), hop_length=1,
+                 normalize_window=False, *, log_eps: Optional[float] = None):
+        super().__init__()
+        self.hop_length = hop_length
+        self.lambd = nn.Parameter(init_lambd)
+        self.device = device
+        self.size = size
+        self.optimized = optimized
+        self.normalize_window = normalize_window
+        self.log_eps = log_eps
+
+    def forward(self, x):
+        dev = _resolve_device(self.device, self.lambd)
+        if dev.type != 'cuda':
+            raise _lib.DmelError(
+                f"SpectrogramLayer lives on {dev}: this implementation is CUDA-only (sm_100a) and has no CPU "
+                "fallback; move the module with .to('cuda')")
+        if x.device != dev:
+            x = x.to(dev, non_blocking=True)
+        s = dmel(x, self.lambd, hop_length=self.hop_length, optimized=self.optimized,
+                 normalize_window=self.normalize_window, n_mels=0, log_eps=self.log_eps)
+        if self.optimized and tuple(s.shape[2:]) != tuple(self.size):
+            # models.py:186,198: the reference allocates `size` and assigns the (F, T) spectrogram into it
+            raise RuntimeError(f"spectrogram of shape {tuple(s.shape[2:])} does not fit size={tuple(self.size)}")
+        return s
+
+    def extra_repr(self):
+        return (f"hop_length={self.hop_length}, optimized={self.optimized}, size={self.size}, "
+                f"normalize_window={self.normalize_window}, log_eps={self.log_eps}")

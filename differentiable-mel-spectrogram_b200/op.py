@@ -1,0 +1,185 @@
+"""The DMEL custom op: host logic + torch.autograd.Function over the C ABI (include/dmel.h).
+
+Host logic mirrored from the reference:
+  * window length  — time_frequency.py:34-43, 60-65: next_power_of_2(int(6*|lambd|)) when
+    `optimized`, else len(x); n_fft = win_length (optimized) or 2*win_length
+    (time_frequency.py:48 / :51).  The reference does this with one device->host sync per
+    sample; here it is one `.item()` per forward for the whole batch.
+  * output geometry — models.py:30 n_time = n_points // hop + 1, rows = n_mels or n_fft/2+1.
+PyTorch only provides device memory and the current stream; all arithmetic on the path is
+in libdmel_b200.so.  Non-CUDA tensors are rejected (no CPU fallback).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from .melbank import DeviceBank, device_bank
+
+
+def shift_bit_length(x) -> int:
+    """time_frequency.py:60-62: smallest power of two >= int(x) (0 -> 2, 1 -> 1)."""
+    xi = int(x)
+    return 1 << (xi - 1).bit_length()
+
+
+def next_power_of_2(x) -> int:
+    """time_frequency.py:64-65."""
+    return shift_bit_length(x)
+
+
+def window_length_from_lambda(lambd_value: float, n_stds: int = 6) -> int:
+    """time_frequency.py:39 evaluated like the reference: the product is an fp32 tensor op
+    (|lambd| is fp32, n_stds a Python int), `int()` truncates."""
+    prod = np.float32(abs(np.float32(lambd_value))) * np.float32(n_stds)
+    return next_power_of_2(prod)
+
+
+@dataclass(frozen=True)
+class Geometry:
+    batch: int
+    n_points: int
+    hop: int
+    win_length: int
+    n_fft: int
+    n_frames: int
+    n_freqs: int
+    rows: int          # n_mels, or n_freqs in spectrogram mode
+    n_mels: int        # 0 in spectrogram mode
+
+
+def resolve_geometry(batch: int, n_points: int, hop: int, lambd_value: float, optimized: bool,
+                     n_mels: int = 0) -> Geometry:
+    if optimized:
+        win = window_length_from_lambda(lambd_value)
+        n_fft = win
+    else:
+        win = int(n_points)
+        n_fft = 2 * win
+    n_freqs = n_fft // 2 + 1
+    return Geometry(int(batch), int(n_points), int(hop), win, n_fft, n_points // hop + 1, n_freqs,
+                    n_mels if n_mels > 0 else n_freqs, n_mels)
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.DmelError(
+            f"{name} is on {t.device}: the B200 DMEL op has no CPU path (device='cpu' layers cannot run; "
+            "use the reference itself for CPU results)")
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+class DmelFunction(torch.autograd.Function):
+    """y = DMEL(x, lambd); saves only x, lambd (and y when the log is fused) plus the small
+    workspace (per-clip means, window, twiddles) — spectra are recomputed in backward."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, lambd: torch.Tensor, geo: Geometry, bank: Optional[DeviceBank],
+                log_eps: float, flags: int, lam_value: float):
+        lib = _lib.load()
+        dev = x.device
+        y = torch.empty((geo.batch, 1, geo.rows, geo.n_frames), dtype=torch.float32, device=dev)
+        ws_bytes = lib.dmel_workspace_bytes(geo.batch, geo.n_fft)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.dmel_forward_f32(
+                x.data_ptr(), geo.batch, geo.n_points, x.stride(0),
+                lam_value, geo.win_length, geo.n_fft, geo.hop,
+                geo.n_mels, bank.ref() if bank is not None else None, float(log_eps),
+                int(flags), y.data_ptr(),
+                ws.data_ptr(), ws_bytes, _stream_ptr(dev))
+        _lib.check(rc, "dmel_forward_f32")
+        ctx.geo, ctx.bank, ctx.log_eps, ctx.flags, ctx.lam_value = geo, bank, float(log_eps), int(flags), lam_value
+        ctx.ws = ws
+        ctx.lambd_shape, ctx.lambd_dtype = lambd.shape, lambd.dtype
+        if log_eps >= 0:
+            ctx.save_for_backward(x, y)
+        else:
+            ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_y: torch.Tensor):
+        lib = _lib.load()
+        geo = ctx.geo
+        saved = ctx.saved_tensors
+        x = saved[0]
+        y = saved[1] if ctx.log_eps >= 0 else None
+        dev = x.device
+        need_dx = ctx.needs_input_grad[0]
+        gy = grad_y.to(torch.float32).contiguous()
+        grad_x = torch.empty((geo.batch, geo.n_points), dtype=torch.float32, device=dev) if need_dx else None
+        grad_lambda = torch.empty((), dtype=torch.float32, device=dev)
+        ws = ctx.ws
+        with torch.cuda.device(dev):
+            rc = lib.dmel_backward_f32(
+                x.data_ptr(), geo.batch, geo.n_points, x.stride(0),
+                ctx.lam_value, geo.win_length, geo.n_fft, geo.hop,
+                geo.n_mels, ctx.bank.ref() if ctx.bank is not None else None, ctx.log_eps,
+                ctx.flags, y.data_ptr() if y is not None else None, gy.data_ptr(),
+                grad_x.data_ptr() if need_dx else None, grad_lambda.data_ptr(),
+                ws.data_ptr(), ws.numel(), 1, _stream_ptr(dev))
+        _lib.check(rc, "dmel_backward_f32")
+        g_lambd = None
+        if ctx.needs_input_grad[1]:
+            g_lambd = grad_lambda.reshape(ctx.lambd_shape).to(ctx.lambd_dtype)
+        return grad_x, g_lambd, None, None, None, None, None
+
+
+def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bool,
+         normalize_window: bool = False, n_mels: int = 0, sample_rate: int = 0, f_min: float = 0.0,
+         f_max: Optional[float] = None, log_eps: Optional[float] = None, remove_mean: bool = True) -> torch.Tensor:
+    """Functional form of both layers.
+
+    x: (B, N) CUDA tensor (fp32; fp64/fp16 inputs are cast to fp32 — the reference's fp64
+    synthetic dataset ends in an fp32 output buffer anyway, models.py:189).  Returns
+    (B, 1, rows, N//hop + 1) fp32, contiguous: the linear (mel) power spectrogram, or its
+    log(. + log_eps) when log_eps is given (the classifiers' energy_normalize, models.py:72).
+    n_mels == 0 selects spectrogram mode (models.py:171-200).
+    """
+    if x.dim() != 2:
+        raise ValueError(f"expected x of shape (batch, n_points), got {tuple(x.shape)}")
+    _require_cuda(x, "x")
+    if lambd.numel() != 1:
+        raise ValueError("lambd must hold exactly one element")
+    if x.dtype != torch.float32:
+        x = x.to(torch.float32)
+    if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
+        x = x.contiguous()
+    if lambd.device != x.device:
+        raise _lib.DmelError(f"lambd on {lambd.device} but x on {x.device}")
+    # the one host sync of the forward (the reference syncs once per sample)
+    lam_value = float(lambd.detach().to(torch.float32).item())
+    B, N = x.shape
+    geo = resolve_geometry(B, N, hop_length, lam_value, optimized, n_mels)
+    lib = _lib.load()
+    if not lib.dmel_nfft_supported(geo.n_fft):
+        raise _lib.DmelError(f"n_fft={geo.n_fft} (lambd={lam_value}) has no kernel")
+    bank = None
+    if n_mels > 0:
+        fmax = f_max if f_max is not None else sample_rate // 2
+        bank = device_bank(geo.n_freqs, f_min, fmax, n_mels, sample_rate, x.device)
+    flags = (_lib.FLAG_NORMALIZE_WINDOW if normalize_window else 0) | (0 if remove_mean else _lib.FLAG_KEEP_MEAN)
+    eps = -1.0 if log_eps is None else float(log_eps)
+    if log_eps is not None and log_eps < 0:
+        raise ValueError("log_eps must be >= 0")
+    return DmelFunction.apply(x, lambd, geo, bank, eps, flags, lam_value)
+
+
+def query_launch(n_points: int, n_fft: int, hop: int, rows: int, which: int = 0) -> Tuple[int, int, int, int]:
+    """(tile_frames, smem_bytes, threads, path) the launcher would use; path 0 = FFT, 1 = DFT."""
+    import ctypes
+    lib = _lib.load()
+    a, b, c, d = (ctypes.c_int32() for _ in range(4))
+    _lib.check(lib.dmel_query_launch(n_points, n_fft, hop, rows, which, ctypes.byref(a), ctypes.byref(b),
+                                     ctypes.byref(c), ctypes.byref(d)), "dmel_query_launch")
+    return a.value, b.value, c.value, d.value

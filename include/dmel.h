@@ -1,0 +1,138 @@
+/* dmel.h — C ABI of the B200-native DMEL hot path (libdmel_b200.so).
+ *
+ * The reference (johnmartinsson/differentiable-mel-spectrogram) has no FFI layer: its
+ * boundary for this path is the torch.nn.Module contract of
+ *     models.py:14-56    MelSpectrogramLayer.__init__/forward
+ *     models.py:171-200  SpectrogramLayer.__init__/forward
+ * which call time_frequency.py:21-58 (Gaussian window + torch.stft + |.|^2),
+ * torchaudio.functional.melscale_fbanks and torch.matmul, followed by
+ * torch.log(s + 1e-10) in the classifier heads (models.py:72-73, 96-97, 125-126,
+ * 156-157) and by autograd's backward of that whole chain (train.py:47).
+ * The entry points below are what a Python (ctypes), C++ or any other host binds to
+ * replace exactly that chain; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - every pointer except the dmel_melbank struct itself is a DEVICE pointer
+ *   - plain pointers and sizes only; no torch types
+ *   - stream-ordered: nothing synchronises the device, nothing is allocated, no
+ *     global mutable state (the caller owns x, y, grads and the workspace)
+ *   - return value: DMEL_OK (0) or a negative dmel_status; never throws / exits
+ *   - fp32 arithmetic throughout ("f32" suffix); dL/dlambda is accumulated in fp64
+ */
+#ifndef DMEL_H_
+#define DMEL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMEL_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DMEL_API __attribute__((visibility("default")))
+#else
+#define DMEL_API
+#endif
+
+#define DMEL_FLAG_NORMALIZE_WINDOW 1
+#define DMEL_FLAG_KEEP_MEAN 2
+
+typedef enum dmel_status {
+    DMEL_OK = 0,
+    DMEL_ERR_NULL_POINTER = -1,
+    DMEL_ERR_BAD_GEOMETRY = -2,      /* B, N, hop, n_fft, win_length, n_mels inconsistent   */
+    DMEL_ERR_UNSUPPORTED_NFFT = -3,  /* n_fft has no kernel (see dmel_nfft_supported)       */
+    DMEL_ERR_WORKSPACE_TOO_SMALL = -4,
+    DMEL_ERR_LAUNCH_FAILED = -5,     /* cudaGetLastError() after a launch was not success   */
+    DMEL_ERR_SMEM_EXCEEDED = -6,     /* no tile size fits the 227 KB shared memory of an SM */
+    DMEL_ERR_BAD_MELBANK = -7
+} dmel_status;
+
+/* Sparse forms of the (n_freqs x n_mels) filterbank that replaces the dense
+ * torch.matmul(spec.T, mel_fb) of models.py:53.  Built once per n_freqs by the host
+ * from the dense matrix (so the weights are bit-identical to the dense ones):
+ *   mel-major (forward gather):  mel m reads bins  mel_k0[m] .. mel_k0[m]+cnt-1,
+ *       cnt = mel_off[m+1]-mel_off[m], weights mel_w[mel_off[m] + i]
+ *   bin-major (backward gather): bin k reads mels  bin_m0[k] .. bin_m0[k]+cnt-1,
+ *       cnt = bin_off[k+1]-bin_off[k], weights bin_w[bin_off[k] + i]
+ * All six arrays are device pointers; the struct itself lives on the host.       */
+typedef struct dmel_melbank {
+    int32_t n_freqs;          /* F = n_fft/2 + 1                                        */
+    int32_t n_mels;           /* M                                                      */
+    const int32_t* mel_k0;    /* [M]                                                    */
+    const int32_t* mel_off;   /* [M+1]                                                  */
+    const float* mel_w;       /* [mel_off[M]]                                           */
+    const int32_t* bin_m0;    /* [F]                                                    */
+    const int32_t* bin_off;   /* [F+1]                                                  */
+    const float* bin_w;       /* [bin_off[F]]                                           */
+} dmel_melbank;
+
+DMEL_API int dmel_abi_version(void);
+DMEL_API const char* dmel_status_string(int status);
+
+/* 1 if a kernel exists for this transform length (radix FFT path for powers of two
+ * 128..4096, direct-DFT path for everything else up to DMEL_MAX_DFT_NFFT), else 0.  */
+DMEL_API int dmel_nfft_supported(int32_t n_fft);
+
+/* time_frequency.py:60-65 next_power_of_2(int(6*|lambda|)) evaluated the way the
+ * reference does (fp32 product, int() truncation, 0 -> 2, 1 -> 1).                  */
+DMEL_API int32_t dmel_window_length_from_lambda(float lambda);
+
+/* Bytes of device scratch a forward/backward pair needs (window, twiddles, per-clip
+ * means, per-clip dx sums, fp64 dL/dlambda accumulator).                            */
+DMEL_API size_t dmel_workspace_bytes(int64_t batch, int32_t n_fft);
+
+/* Forward:  y[b,0,m,t] of models.py:33-56 (n_mels > 0) or models.py:182-200
+ * (n_mels == 0: "spectrogram mode", rows are the n_fft/2+1 frequency bins).
+ *   x           [batch, n_points] fp32, row stride x_row_stride elements
+ *   lambda      the layer's parameter `lambd` (signed; |.| is taken as models.py:38)
+ *   win_length  Gaussian window length: next_power_of_2(6|lambda|) when optimized,
+ *               n_points otherwise (time_frequency.py:34-43)
+ *   n_fft       win_length (optimized) or 2*win_length (time_frequency.py:48/51)
+ *   hop         hop_length; frames T = n_points/hop + 1 (models.py:30), center=True,
+ *               pad_mode='constant'
+ *   bank        NULL iff n_mels == 0
+ *   log_eps     >= 0: y = log(mel + log_eps) fused (models.py:72-73); < 0: linear
+ *   flags       DMEL_FLAG_NORMALIZE_WINDOW: time_frequency.py:25-30 `norm`;
+ *               DMEL_FLAG_KEEP_MEAN: skip the per-clip mean removal of models.py:38 (what a
+ *               direct caller of time_frequency.differentiable_spectrogram gets)
+ *   y           [batch, 1, rows, T] fp32 contiguous, rows = n_mels or n_fft/2+1
+ *   workspace   >= dmel_workspace_bytes(batch, n_fft); filled here (means, window,
+ *               twiddles) and reusable by dmel_backward_f32 with prepared = 1      */
+DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
+                     float lambda, int32_t win_length, int32_t n_fft, int32_t hop,
+                     int32_t n_mels, const dmel_melbank* bank, float log_eps,
+                     int32_t flags, float* y,
+                     void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Backward of the same chain (what autograd does for train.py:47).
+ *   y            forward output; read only when log_eps >= 0 (may be NULL otherwise)
+ *   grad_y       dL/dy, same shape as y
+ *   grad_x       [batch, n_points] contiguous, or NULL: skip dL/dx entirely (the
+ *                reference's training case — x is data, only `lambd` is a parameter)
+ *   grad_lambda  one fp32: dL/dlambda (includes sign(lambda) from torch.abs)
+ *   prepared     1: workspace still holds what dmel_forward_f32 wrote for the same
+ *                (x, lambda, geometry); 0: recompute means/window/twiddles first    */
+DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
+                      float lambda, int32_t win_length, int32_t n_fft, int32_t hop,
+                      int32_t n_mels, const dmel_melbank* bank, float log_eps,
+                      int32_t flags, const float* y, const float* grad_y,
+                      float* grad_x, float* grad_lambda,
+                      void* workspace, size_t workspace_bytes, int32_t prepared,
+                      void* cuda_stream);
+
+/* Introspection for tests / benchmarks: tile size (frames per CTA), dynamic shared
+ * memory and threads per CTA the launcher would pick.  which: 0 fwd, 1 bwd (dx+dlambda),
+ * 2 bwd (dlambda only).  Returns DMEL_OK or an error.                               */
+DMEL_API int dmel_query_launch(int64_t n_points, int32_t n_fft, int32_t hop, int32_t rows, int32_t which,
+                      int32_t* tile_frames, int32_t* smem_bytes, int32_t* threads, int32_t* path);
+
+#define DMEL_MAX_DFT_NFFT 32768
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMEL_H_ */

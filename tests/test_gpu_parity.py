@@ -1,0 +1,259 @@
+"""Parity of the CUDA path (through the C ABI, via the drop-in layers / dmel op) against
+  (1) tests/golden — outputs of the unmodified reference, (2) the CPU oracle on seeded inputs,
+  (3) size-independent properties at BASELINE.json's full sizes.
+Tolerances are north_star's: log-mel rel 1e-4 / abs 1e-5; dL/dx, dL/dlambda rel 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+import dmel_b200 as dm
+from conftest import golden_names, load_golden, oracle_kwargs, rel_err
+from oracle import dmel_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+Y_RTOL, Y_ATOL = 1e-4, 1e-5
+G_RTOL = 1e-3
+EPS = 1e-10
+
+
+def op_kwargs(meta):
+    kw = dict(hop_length=meta["hop"], optimized=meta["opt"], normalize_window=meta["norm"])
+    if meta["kind"] == "mel":
+        kw.update(n_mels=meta["M"], sample_rate=meta["sr"])
+    return kw
+
+
+def run_cuda(dev, x, lam, G, use_log, fused, need_dx=True, **kw):
+    xx = torch.as_tensor(x).to(dev).clone().requires_grad_(need_dx)
+    ll = torch.tensor(float(lam), device=dev, requires_grad=True)
+    if use_log and fused:
+        out = dm.dmel(xx, ll, log_eps=EPS, **kw)
+    else:
+        out = dm.dmel(xx, ll, **kw)
+        if use_log:
+            out = torch.log(out + EPS)
+    (out * torch.as_tensor(G).to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    return (out.detach().cpu().numpy(), xx.grad.detach().cpu().numpy() if need_dx else None, float(ll.grad))
+
+
+def check_y(got, want, lin):
+    if lin:
+        # linear power: same relative bar, absolute floor scaled to the data (|y| spans decades)
+        np.testing.assert_allclose(got, want, rtol=Y_RTOL, atol=Y_ATOL * float(np.abs(want).max()))
+    else:
+        np.testing.assert_allclose(got, want, rtol=Y_RTOL, atol=Y_ATOL)
+
+
+def check_grads(dx, dlam, dx_ref, dlam_ref, dlam_ref64=None):
+    assert rel_err(dx, dx_ref) < G_RTOL
+    np.testing.assert_allclose(dx, dx_ref, rtol=G_RTOL, atol=G_RTOL * float(np.abs(dx_ref).max()))
+    ok = abs(dlam - dlam_ref) <= G_RTOL * abs(dlam_ref)
+    if not ok and dlam_ref64 is not None:  # the reference's own fp32 noise can exceed 1e-3 under cancellation
+        ok = abs(dlam - dlam_ref64) <= G_RTOL * abs(dlam_ref64)
+    assert ok, (dlam, dlam_ref, dlam_ref64)
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("tag,fused", [("lin", False), ("log", True), ("log", False)])
+def test_matches_reference_golden(cuda_device, name, tag, fused):
+    g = load_golden(name)
+    y, dx, dlam = run_cuda(cuda_device, g["x"], g["lam"], g["G"], tag == "log", fused, **op_kwargs(g["meta"]))
+    assert y.dtype == np.float32 and y.shape == g[f"y_{tag}"].shape
+    check_y(y, g[f"y_{tag}"], tag == "lin")
+    check_grads(dx, dlam, g[f"dx_{tag}"], float(g[f"dlam_{tag}"]), float(g[f"dlam64_{tag}"]))
+    # and against the fp64 run of the reference (tie-breaker: we should be at least as close to the truth)
+    assert rel_err(dx, g[f"dx64_{tag}"]) < G_RTOL
+
+
+@pytest.mark.parametrize("name", ["mel_L512_am", "mel_L2048_44k", "mel_L64_dft", "spec_tf_N64_small_lam"])
+def test_lambda_only_backward_equals_full_backward(cuda_device, name):
+    g = load_golden(name)
+    kw = op_kwargs(g["meta"])
+    _, _, full = run_cuda(cuda_device, g["x"], g["lam"], g["G"], True, True, need_dx=True, **kw)
+    _, dx, only = run_cuda(cuda_device, g["x"], g["lam"], g["G"], True, True, need_dx=False, **kw)
+    assert dx is None
+    assert abs(full - only) <= 1e-6 * abs(full)
+
+
+def _oracle_case(dev, B, N, sr, hop, M, lam, seed, use_log=True, norm=False, optimized=True, x_dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, N, generator=g).to(x_dtype)
+    kw_o = dict(hop=hop, optimized=optimized, norm=norm, n_mels=M, sample_rate=sr)
+    kw_c = dict(hop_length=hop, optimized=optimized, normalize_window=norm, n_mels=M, sample_rate=sr)
+    with torch.no_grad():
+        shape = orc.port_forward_batched(x[:1].float(), torch.tensor(lam), **kw_o).shape
+    G = torch.randn((B,) + tuple(shape[1:]), generator=g)
+    want = orc.port_forward_backward(x.float(), lam, G, use_log=use_log, batched=True, **kw_o)
+    got = run_cuda(dev, x, lam, G, use_log, True, **kw_c)
+    return got, want
+
+
+# BASELINE.json configs at sizes the oracle finishes in seconds (full AM batch; ESC / large-batch clips at reduced B)
+@pytest.mark.parametrize("B,N,sr,hop,M,lam", [
+    (256, 8000, 8000, 80, 64, 8000 * 0.035 / 6),        # configs[1] audio_mnist, full size, n_fft 512
+    (4, 220500, 44100, 441, 128, 44100 * 0.035 / 6),    # configs[2] esc50 clip shape, n_fft 2048
+    (4, 220500, 44100, 441, 128, 44100 * 0.010 / 6),    # esc50 lambda sweep: 10 ms -> n_fft 512
+    (16, 8000, 8000, 80, 64, 0.75 * 256 / 6),           # configs[3] window sweep n_fft 256
+    (16, 8000, 8000, 80, 64, 0.75 * 1024 / 6),          # n_fft 1024
+    (16, 8000, 8000, 80, 64, 0.75 * 2048 / 6),          # n_fft 2048
+    (16, 8000, 8000, 80, 64, 0.75 * 4096 / 6),          # n_fft 4096
+    (16, 8000, 8000, 80, 64, 8000 * 0.010 / 6),         # reference grid 10 ms -> n_fft 128
+    (16, 8000, 8000, 80, 64, 8000 * 0.300 / 6),         # reference grid 300 ms -> n_fft 4096
+    (3, 160000, 16000, 160, 128, 16000 * 0.035 / 6),    # configs[4] large-batch clip shape, n_fft 1024
+])
+def test_matches_oracle_on_baseline_shapes(cuda_device, B, N, sr, hop, M, lam):
+    (y, dx, dlam), (y0, dx0, dlam0) = _oracle_case(cuda_device, B, N, sr, hop, M, lam, seed=1234)
+    check_y(y, y0, False)
+    check_grads(dx, dlam, dx0, dlam0)
+
+
+def test_time_frequency_config_spectrogram_layer(cuda_device):
+    """configs[0]: SpectrogramLayer, optimized=False, hop 1, N=256 -> n_fft 512, out (B,1,257,257); fp64 inputs."""
+    for N, lam in [(256, 6.38), (128, 0.2 * 6.38), (128, 5 * 6.38)]:
+        g = torch.Generator().manual_seed(N)
+        x = torch.randn(8, N, generator=g, dtype=torch.float64)
+        G = torch.randn(8, 1, N + 1, N + 1, generator=g)
+        want = orc.port_forward_backward(x.float(), lam, G, use_log=False, batched=True, hop=1, optimized=False)
+        layer = dm.SpectrogramLayer(torch.tensor(lam), device="cuda:0", optimized=False, size=(N + 1, N + 1), hop_length=1).to(cuda_device)
+        xx = x.to(cuda_device).requires_grad_(True)
+        s = layer(xx)
+        assert s.shape == (8, 1, N + 1, N + 1) and s.dtype == torch.float32 and s.is_contiguous()
+        (s * G.to(cuda_device)).sum().backward()
+        check_y(s.detach().cpu().numpy(), want[0], True)
+        check_grads(xx.grad.cpu().numpy(), float(layer.lambd.grad), want[1], want[2])
+        assert xx.grad.dtype == torch.float64  # gradient comes back in the caller's dtype
+
+
+def test_full_size_properties_esc50_and_large_batch(cuda_device):
+    """At BASELINE's full sizes the oracle is too slow; use exact, size-independent properties instead."""
+    dev = cuda_device
+    for (B, N, sr, hop, M, lam) in [(128, 220500, 44100, 441, 128, 257.25), (256, 160000, 16000, 160, 128, 93.33)]:
+        g = torch.Generator().manual_seed(7)
+        x = torch.randn(B, N, generator=g).to(dev)
+        ll = torch.tensor(lam, device=dev, requires_grad=True)
+        kw = dict(hop_length=hop, optimized=True, n_mels=M, sample_rate=sr)
+        y = dm.dmel(x, ll, **kw)
+        assert y.shape == (B, 1, M, N // hop + 1) and y.is_contiguous() and torch.isfinite(y).all()
+        # (a) clips are independent: permuting the batch permutes the output bit-exactly
+        perm = torch.randperm(B, generator=g).to(dev)
+        assert torch.equal(dm.dmel(x[perm], ll, **kw), y[perm])
+        # (b) sharding the batch (what the multi-GPU path does) changes nothing, bit for bit
+        h = B // 2
+        assert torch.equal(torch.cat([dm.dmel(x[:h], ll, **kw), dm.dmel(x[h:], ll, **kw)]), y)
+        # (c) power is quadratic: scaling by 2 scales every output by exactly 4 in fp32; DC offset is removed
+        assert torch.equal(dm.dmel(2.0 * x, ll, **kw), 4.0 * y)
+        y_dc = dm.dmel(x + 3.0, ll, **kw)
+        assert rel_err(y_dc.cpu().numpy(), y.cpu().numpy()) < 1e-4
+        # (d) d/dlambda accumulated over shards equals the whole-batch gradient; dx rows have zero mean
+        G = torch.randn(y.shape, generator=torch.Generator().manual_seed(9)).to(dev)
+        xx = x.clone().requires_grad_(True)
+        yl = dm.dmel(xx, ll, log_eps=EPS, **kw)
+        (yl * G).sum().backward()
+        whole, dx = float(ll.grad), xx.grad
+        ll.grad = None
+        for sl in (slice(0, h), slice(h, B)):
+            (dm.dmel(x[sl], ll, log_eps=EPS, **kw) * G[sl]).sum().backward()
+        assert abs(float(ll.grad) - whole) <= 1e-5 * abs(whole)
+        assert float(dx.mean(dim=1).abs().max()) <= 1e-4 * float(dx.abs().max())
+        # (e) a few clips against the oracle
+        sub = [0, B // 2, B - 1]
+        want = orc.port_forward_backward(x[sub].cpu(), lam, G[sub].cpu(), use_log=True, batched=True, hop=hop,
+                                         optimized=True, n_mels=M, sample_rate=sr)
+        check_y(yl[sub].detach().cpu().numpy(), want[0], False)
+        assert rel_err(dx[sub].cpu().numpy(), want[1]) < G_RTOL
+        del x, y, G, xx, yl, dx
+        torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("B,N,hop,lam,M", [
+    (1, 50, 80, 46.667, 8),      # N < hop: a single frame, clip shorter than half a window
+    (2, 79, 80, 20.0, 8),        # T = 1
+    (3, 161, 80, 46.667, 16),    # T = 3 (odd): last pair has one real frame
+    (2, 1000, 600, 13.333, 8),   # hop > n_fft: frames leave gaps in x (dx there is only -mean)
+    (5, 4001, 1, 23.0, 12),      # hop 1, many tiles
+    (2, 2500, 33, 90.0, 24),     # n_fft 1024 with an odd hop
+])
+def test_edge_geometries_against_oracle(cuda_device, B, N, hop, lam, M):
+    (y, dx, dlam), (y0, dx0, dlam0) = _oracle_case(cuda_device, B, N, 8000, hop, M, lam, seed=N + hop)
+    check_y(y, y0, False)
+    check_grads(dx, dlam, dx0, dlam0)
+
+
+def test_strided_rows_fp16_input_and_negative_lambda(cuda_device):
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    big = torch.randn(4, 3000, generator=g)
+    x = big[:, 100:1700]                                   # row stride 3000, offset start
+    G = torch.randn(4, 1, 32, 21, generator=g)
+    kw_o = dict(hop=80, optimized=True, n_mels=32, sample_rate=8000)
+    want = orc.port_forward_backward(x.contiguous(), -46.667, G, use_log=True, batched=True, **kw_o)
+    xb = big.to(dev)
+    xs = xb[:, 100:1700].requires_grad_(True)
+    ll = torch.tensor(-46.667, device=dev, requires_grad=True)
+    y = dm.dmel(xs, ll, hop_length=80, optimized=True, n_mels=32, sample_rate=8000, log_eps=EPS)
+    (y * G.to(dev)).sum().backward()
+    check_y(y.detach().cpu().numpy(), want[0], False)
+    check_grads(xs.grad.cpu().numpy(), float(ll.grad), want[1], want[2])
+    assert want[2] * float(ll.grad) > 0
+    # half-precision storage is converted on entry
+    xh = x.to(torch.float16)
+    yh = dm.dmel(xh.to(dev), ll, hop_length=80, optimized=True, n_mels=32, sample_rate=8000)
+    w = orc.port_forward_batched(xh.float(), torch.tensor(46.667), **kw_o)
+    check_y(yh.detach().cpu().numpy(), w.numpy(), True)
+
+
+def test_all_zero_input_hits_the_log_floor_exactly(cuda_device):
+    layer = dm.MelSpectrogramLayer(torch.tensor(46.667), n_mels=64, n_points=1600, sample_rate=8000, hop_length=80,
+                                   device="cuda:0", optimized=True, log_eps=EPS).to(cuda_device)
+    y = layer(torch.zeros(2, 1600, device=cuda_device) + 5.0)   # constant clip: mean removal leaves silence
+    assert torch.all(y == torch.log(torch.tensor(EPS, device=cuda_device)))
+
+
+def test_drop_in_module_contract(cuda_device):
+    """What the reference's heads do with the layer (models.py:59-78, main.py:27,36-48, utils.py:269)."""
+    dev = cuda_device
+
+    class MelLinear(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.spectrogram_layer = dm.MelSpectrogramLayer(torch.tensor(46.667), n_mels=64, n_points=8000, sample_rate=8000,
+                                                            hop_length=80, device="cuda:0", optimized=True)
+            self.fc = torch.nn.Linear(64 * 101, 10)
+
+        def forward(self, x):
+            s = self.spectrogram_layer(x)
+            s = torch.log(s + 1e-10)
+            return self.fc(s.view(-1, 64 * 101)), s
+
+    net = MelLinear().to(dev)
+    names = [n for n, _ in net.named_parameters()]
+    assert "spectrogram_layer.lambd" in names
+    x = torch.randn(8, 8000, device=dev)
+    logits, s = net(x)
+    assert s.shape == (8, 1, 64, 101) and logits.shape == (8, 10)
+    torch.nn.functional.cross_entropy(logits, torch.arange(8, device=dev) % 10).backward()
+    assert net.spectrogram_layer.lambd.grad is not None and torch.isfinite(net.spectrogram_layer.lambd.grad)
+    assert isinstance(net.spectrogram_layer.lambd.item(), float)
+    sd = net.state_dict()
+    net2 = MelLinear().to(dev)
+    net2.load_state_dict(sd)
+    assert torch.equal(net2(x)[1], s)
+    # frozen layer (trainable=False, main.py:27): no graph through the op
+    net.spectrogram_layer.requires_grad_(False)
+    assert not net(x)[1].requires_grad
+    # lambda moved by the optimiser -> n_fft follows it (512 -> 1024)
+    with torch.no_grad():
+        net.spectrogram_layer.lambd.fill_(90.0)
+    assert net(x)[1].shape == (8, 1, 64, 101)
+
+
+def test_time_frequency_function_mirror(cuda_device):
+    dev = cuda_device
+    x = torch.randn(1000, generator=torch.Generator().manual_seed(5))
+    want = orc._spectrogram_1d(x, torch.tensor(23.0), True, 50, False)
+    got, w = dm.differentiable_spectrogram(x.to(dev), torch.tensor(23.0, device=dev), optimized=True, hop_length=50,
+                                           return_window=True)
+    check_y(got.cpu().numpy(), want.numpy(), True)
+    np.testing.assert_allclose(w.cpu().numpy(), orc.gaussian_window(torch.tensor(23.0), 256, False).numpy(), rtol=1e-6)

@@ -1,0 +1,127 @@
+"""CPU-side checks: host logic mirrored from the reference, filterbank packing, and that the C-ABI library
+loads and exports every symbol include/dmel.h declares (no compute calls — there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import dmel_b200 as dm
+from conftest import ROOT
+from oracle import dmel_oracle as orc
+
+
+def test_library_loads_and_exports_header_symbols():
+    lib = dm.load()
+    header = open(os.path.join(ROOT, "include", "dmel.h")).read()
+    declared = set(re.findall(r"DMEL_API[^;(]*?\b(dmel_\w+)\s*\(", header))
+    assert declared == set(dm._lib.EXPORTED_SYMBOLS), declared ^ set(dm._lib.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.dmel_abi_version() == 1
+    assert lib.dmel_status_string(0) == b"ok"
+    assert b"n_fft" in lib.dmel_status_string(-3)
+
+
+def test_window_length_python_and_c_agree_with_reference_rule():
+    lib = dm.load()
+    rng = np.random.default_rng(0)
+    lams = list(rng.uniform(0, 700, 300)) + [0.0, 0.16, 0.17, 1 / 3, 0.34, 42.6666, 42.67, 85.33, 85.34, 13.333, 46.667, 400.0,
+                                           -46.667, 682.6, 682.7]
+    for lam in lams:
+        want = orc.next_power_of_2(np.float32(abs(np.float32(lam))) * np.float32(6))
+        assert dm.window_length_from_lambda(lam) == want
+        assert lib.dmel_window_length_from_lambda(ctypes.c_float(lam)) == want
+    assert dm.next_power_of_2(0) == 2 and dm.next_power_of_2(1) == 1  # time_frequency.py:60-65 edge cases
+
+
+def test_geometry_follows_reference():
+    g = dm.resolve_geometry(256, 8000, 80, 46.667, True, 64)
+    assert (g.win_length, g.n_fft, g.n_frames, g.n_freqs, g.rows) == (512, 512, 101, 257, 64)
+    g = dm.resolve_geometry(128, 128, 1, 6.38, False, 0)        # time_frequency search space
+    assert (g.win_length, g.n_fft, g.n_frames, g.rows) == (128, 256, 129, 129)
+    g = dm.resolve_geometry(128, 220500, 441, 257.25, True, 128)
+    assert (g.n_fft, g.n_frames) == (2048, 501)
+
+
+@pytest.mark.parametrize("F,M,sr", [(257, 64, 8000), (65, 64, 8000), (1025, 128, 44100), (513, 128, 16000), (129, 16, 8000)])
+def test_melbank_bit_identical_to_torchaudio_and_pack_roundtrip(F, M, sr):
+    import warnings
+    torchaudio = pytest.importorskip("torchaudio")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = torchaudio.functional.melscale_fbanks(n_freqs=F, f_min=0, f_max=sr // 2, n_mels=M, sample_rate=sr)
+    got = dm.melscale_fbanks_htk(F, 0, sr // 2, M, sr)
+    assert torch.equal(got, want)
+    assert torch.equal(orc.mel_filterbank(F, 0, sr // 2, M, sr), want)
+    from importlib import import_module
+    mb = import_module("differentiable-mel-spectrogram_b200.melbank")
+    p = mb.pack_bank(got.numpy())
+    a, b = mb.unpack_bank(p)
+    assert np.array_equal(a, got.numpy()) and np.array_equal(b, got.numpy())
+    assert (p.bin_off[1:] - p.bin_off[:-1]).max() <= 2          # <= 2 taps per bin
+
+
+def test_pack_bank_generic_matrix():
+    from importlib import import_module
+    mb = import_module("differentiable-mel-spectrogram_b200.melbank")
+    rng = np.random.default_rng(1)
+    fb = rng.random((9, 5)).astype(np.float32)
+    fb[0] = 0
+    fb[:, 3] = 0
+    fb[4, 1] = 0
+    a, b = mb.unpack_bank(mb.pack_bank(fb))
+    assert np.array_equal(a, fb) and np.array_equal(b, fb)
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_the_device():
+    lib = dm.load()
+    f = lib.dmel_forward_f32
+    # null x
+    assert f(None, 1, 100, 100, 10.0, 64, 64, 10, 0, None, -1.0, 0, 1, 1, 1 << 20, None) == -1
+    # n_fft < win_length
+    assert f(8, 1, 100, 100, 10.0, 128, 64, 10, 0, None, -1.0, 0, 8, 8, 1 << 20, None) == -2
+    # mel mode without a bank
+    assert f(8, 1, 100, 100, 10.0, 64, 64, 10, 4, None, -1.0, 0, 8, 8, 1 << 20, None) == -1
+    # workspace too small
+    assert f(8, 1, 100, 100, 10.0, 64, 64, 10, 0, None, -1.0, 0, 8, 8, 16, None) == -4
+    # odd n_fft has no kernel
+    assert lib.dmel_nfft_supported(255) == 0 and lib.dmel_nfft_supported(512) == 1 and lib.dmel_nfft_supported(200) == 1
+    assert lib.dmel_workspace_bytes(256, 512) >= 64 + 512 * 12 + 256 * 12
+
+
+def test_launch_plans_fit_shared_memory():
+    for (N, L, hop, rows) in [(8000, 512, 80, 64), (220500, 2048, 441, 128), (160000, 1024, 160, 128), (8000, 4096, 80, 64),
+                              (8000, 128, 80, 64), (256, 512, 1, 257), (128, 256, 1, 129), (8000, 256, 80, 64)]:
+        for which in (0, 1, 2):
+            tt, smem, threads, path = dm.query_launch(N, L, hop, rows, which)
+            assert path == 0 and smem <= 227 * 1024 and tt % 2 == 0 and threads in (32, 64, 128, 256)
+    assert dm.query_launch(100, 200, 5, 101, 1)[3] == 1           # non power of two -> direct DFT path
+
+
+def test_layers_keep_the_reference_contract_and_refuse_cpu():
+    layer = dm.MelSpectrogramLayer(torch.tensor(46.667), n_mels=64, n_points=8000, sample_rate=8000, hop_length=80,
+                                   device="cpu", optimized=True, normalize_window=False)
+    assert list(layer.state_dict().keys()) == ["lambd"] and layer.lambd.dim() == 0
+    assert (layer.n_freq, layer.n_time, layer.f_max, layer.f_min) == (64, 101, 4000, 0)
+    assert [n for n, _ in layer.named_parameters()] == ["lambd"]
+    layer.requires_grad_(False)
+    assert not layer.lambd.requires_grad
+    with pytest.raises(dm.DmelError, match="no CPU"):
+        layer(torch.zeros(2, 8000))
+    spec = dm.SpectrogramLayer(torch.tensor(6.38), device="cpu", optimized=False, size=(129, 129), hop_length=1)
+    assert list(spec.state_dict().keys()) == ["lambd"]
+    with pytest.raises(dm.DmelError, match="no CPU"):
+        spec(torch.zeros(2, 128))
+    with pytest.raises(dm.DmelError):
+        dm.dmel(torch.zeros(2, 128), torch.tensor(6.38), hop_length=1, optimized=False)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "differentiable-mel-spectrogram_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("no oracle", ""), fn
