@@ -1,0 +1,462 @@
+#!/usr/bin/env python
+"""bench.py — DMEL forward+backward throughput (audio-seconds per second) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload audio_mnist] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one fused forward + one fused backward (dL/dx AND dL/dlambda, log fused, eps 1e-10) over one
+batch of synthetic clips of the named BASELINE.json shape; with N > 1 every rank runs the same per-GPU batch
+(weak scaling) and the step ends with the one collective of the path: an NCCL all-reduce of the scalar
+dL/dlambda.  Prints ONE JSON line (rank 0).
+
+  value      whole-job audio-s/s, inputs resident in HBM, C-ABI calls replayed from a CUDA graph
+             (the small shapes are launch-bound otherwise); buffers rotate over a set > 2x L2
+  e2e        same metric through the public nn.Module (MelSpectrogramLayer.forward + .backward) from
+             PINNED HOST clips: H2D of x every step and D2H of the step's scalar result inside the timed region
+  roofline   dominant kernel: algorithmic bytes per launch / its mean CUDA-event duration, vs the measured
+             HBM copy peak in MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle port of the reference path (oracle/dmel_oracle.py: per-sample loop, torch.stft,
+             filterbank rebuilt per sample, autograd backward) timed on this box's host cores on a bounded sample
+`--impl reference` times only that CPU port (the reference is pure Python and /root/reference does not travel to
+the GPU box; the port is pinned to the reference's outputs by tests/test_oracle_golden.py).
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "dmel_fwd_bwd_audio_seconds_per_second"
+UNIT = "audio-s/s"
+LOG_EPS = 1e-10
+L2_BYTES = 126 * 1024 * 1024
+
+
+def workload(name):
+    """BASELINE.json configs -> concrete synthetic shapes. B is the per-GPU batch."""
+    if name == "audio_mnist":      # configs[1]: 1 s clips, batch 256, n_fft 512, 64 mels
+        return dict(B=256, N=8000, sr=8000, hop=80, M=64, lam=8000 * 0.035 / 6, n_fft=512)
+    if name == "esc50":            # configs[2]: 5 s @ 44.1 kHz, batch 128, n_fft 2048, 128 mels
+        return dict(B=128, N=220500, sr=44100, hop=441, M=128, lam=44100 * 0.035 / 6, n_fft=2048)
+    if name == "large_batch":      # configs[4]: 8192 x 10 s @ 16 kHz over 8 GPUs = 1024 clips per GPU
+        return dict(B=1024, N=160000, sr=16000, hop=160, M=128, lam=16000 * 0.035 / 6, n_fft=1024)
+    if name.startswith("sweep_"):  # configs[3]: batch 512, n_fft 128..4096, lambda = 0.75 n_fft / 6
+        n_fft = int(name.split("_")[1])
+        return dict(B=512, N=8000, sr=8000, hop=80, M=64, lam=0.75 * n_fft / 6, n_fft=n_fft)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def algorithmic_bytes(w, which):
+    """compulsory fp32 traffic of a perfectly fused implementation, per batch."""
+    N, M, T, B = w["N"], w["M"], w["N"] // w["hop"] + 1, w["B"]
+    per_clip = {"fwd": 4 * (N + M * T), "bwd": 4 * (2 * N + M * T), "step": 4 * (3 * N + 2 * M * T)}[which]
+    return per_clip * B
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed regions run."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [v.strip() for v in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0]))
+                mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            # median over the samples taken under load (upper half: the idle gaps between regions read low)
+            s = sorted(sm)
+            out.update(sm_mhz=s[len(s) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_rate(w, budget_s, threads):
+    """Oracle port (reference structure) fwd+bwd with dx and dlambda on a bounded sample; best of the
+    repetitions that fit in ~budget_s.  Returns (audio-s/s, clips in the sample, repetitions, seconds/clip)."""
+    import torch
+    from oracle import dmel_oracle as orc
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1234)
+    T = w["N"] // w["hop"] + 1
+    kw = dict(hop=w["hop"], optimized=True, norm=False, n_mels=w["M"], sample_rate=w["sr"])
+
+    def one_pass(x, G):
+        xx = x.clone().requires_grad_(True)
+        lam = torch.tensor(w["lam"], requires_grad=True)
+        s = orc.port_forward(xx, lam, **kw)
+        (torch.log(s + LOG_EPS) * G).sum().backward()
+        return float(lam.grad)
+
+    x1 = torch.randn(2, w["N"], generator=g)
+    G1 = torch.randn(2, 1, w["M"], T, generator=g)
+    one_pass(x1, G1)                                   # warm-up (thread pools, FFT plans)
+    t0 = time.perf_counter()
+    one_pass(x1, G1)
+    per_clip = (time.perf_counter() - t0) / 2
+    n = int(max(2, min(w["B"], (budget_s / 3.0) / max(per_clip, 1e-6))))
+    x = torch.randn(n, w["N"], generator=g)
+    G = torch.randn(n, 1, w["M"], T, generator=g)
+    best, reps, t_start = float("inf"), 0, time.perf_counter()
+    while reps < 5 and (reps == 0 or time.perf_counter() - t_start < budget_s):
+        t0 = time.perf_counter()
+        one_pass(x, G)
+        best = min(best, time.perf_counter() - t0)
+        reps += 1
+    return n * (w["N"] / w["sr"]) / best, n, reps, best / n
+
+
+def run_reference_arm(args, w):
+    """`--impl reference`: the CPU implementation of the path on the host cores, same metric/config keys."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import dmel_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    T = w["N"] // w["hop"] + 1
+    kw = dict(hop=w["hop"], optimized=True, norm=False, n_mels=w["M"], sample_rate=w["sr"])
+    g = torch.Generator().manual_seed(1234)
+    # size the per-step sample so that (steps + warmup) steps end within ~2 minutes
+    rate, _, _, per_clip = cpu_port_rate(w, 4.0, cores)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    n = int(max(1, min(w["B"], budget / per_clip)))
+    x = torch.randn(n, w["N"], generator=g)
+    G = torch.randn(n, 1, w["M"], T, generator=g)
+
+    def step():
+        xx = x.clone().requires_grad_(True)
+        lam = torch.tensor(w["lam"], requires_grad=True)
+        s = orc.port_forward(xx, lam, **kw)
+        (torch.log(s + LOG_EPS) * G).sum().backward()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = args.steps * n * (w["N"] / w["sr"]) / dt
+    sample = f"{n} of {w['B']} clips per step (serial per-sample loop: cost linear in clips)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, w, extra={"device": "cpu", "sample": sample}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, w, extra=None):
+    c = {"workload": args.workload, "per_gpu_batch": w["B"], "n_points": w["N"], "sample_rate": w["sr"],
+         "hop_length": w["hop"], "n_mels": w["M"], "n_fft": w["n_fft"], "lambda": w["lam"],
+         "mode": "forward+backward (dL/dx and dL/dlambda), fused log eps=1e-10, optimized=True"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--workload", default="audio_mnist")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch the resident loop eagerly instead of from a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
+    args = ap.parse_args()
+    w = workload(args.workload)
+    audio_s = w["B"] * w["N"] / w["sr"]
+    if args.steps is None:
+        # default: ~1.5 s of device time at ~3e6 audio-s/s, so the clock sampler sees the run
+        args.steps = int(min(5000, max(20, 4.0e6 / audio_s)))
+    if args.warmup is None:
+        args.warmup = max(3, min(50, args.steps // 10))
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        return run_reference_arm(args, w)
+
+    import torch
+    import torch.distributed as dist
+    import dmel_b200 as dm
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = dm.load()
+
+    B, N, sr, hop, M, lam = w["B"], w["N"], w["sr"], w["hop"], w["M"], w["lam"]
+    T = N // hop + 1
+    geo = dm.resolve_geometry(B, N, hop, lam, True, M)
+    assert geo.n_fft == w["n_fft"], (geo.n_fft, w["n_fft"])
+    from importlib import import_module
+    bank = import_module("differentiable-mel-spectrogram_b200.melbank").device_bank(geo.n_freqs, 0.0, sr // 2, M, sr, dev)
+
+    # rotating buffer sets: total footprint > 2 x L2 so no step finds its inputs in cache
+    set_bytes = 4 * (2 * B * N + 2 * B * M * T)
+    R = max(2, math.ceil(2.2 * L2_BYTES / set_bytes))
+    R = min(R, args.steps)
+    while args.steps % R:
+        R += 1
+    ws_bytes = lib.dmel_workspace_bytes(B, geo.n_fft)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ggen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    xs = [torch.randn(B, N, device=dev, generator=gen) for _ in range(R)]
+    Gs = [torch.randn(B, 1, M, T, device=dev, generator=ggen) for _ in range(R)]
+    ys = [torch.empty(B, 1, M, T, device=dev) for _ in range(R)]
+    dxs = [torch.empty(B, N, device=dev) for _ in range(R)]
+    dls = [torch.zeros((), device=dev) for _ in range(R)]
+    wss = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in range(R)]
+
+    def resident_step(i):
+        s = i % R
+        st = int(torch.cuda.current_stream(dev).cuda_stream)
+        rc = lib.dmel_forward_f32(xs[s].data_ptr(), B, N, N, lam, geo.win_length, geo.n_fft, hop, M, bank.ref(), LOG_EPS, 0,
+                                  ys[s].data_ptr(), wss[s].data_ptr(), ws_bytes, st)
+        assert rc == 0, lib.dmel_status_string(rc)
+        rc = lib.dmel_backward_f32(xs[s].data_ptr(), B, N, N, lam, geo.win_length, geo.n_fft, hop, M, bank.ref(), LOG_EPS, 0,
+                                   ys[s].data_ptr(), Gs[s].data_ptr(), dxs[s].data_ptr(), dls[s].data_ptr(),
+                                   wss[s].data_ptr(), ws_bytes, 1, st)
+        assert rc == 0, lib.dmel_status_string(rc)
+        if world > 1:
+            dist.all_reduce(dls[s])            # the path's only collective: sum of the scalar lambda gradient
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # warm-up (eager), then optional graph capture of one rotation
+    for i in range(args.warmup):
+        resident_step(i)
+    torch.cuda.synchronize(dev)
+    use_graph = not args.no_graph
+    graph = None
+    if use_graph:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for i in range(R):
+                    resident_step(i)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for i in range(R):
+                    resident_step(i)
+            graph.replay()
+            torch.cuda.synchronize(dev)
+        except Exception as e:  # capture of the NCCL call can fail on some stacks: run eagerly, and say so
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize(dev)
+
+    def resident_loop(k):
+        if graph is not None:
+            for _ in range(k // R):
+                graph.replay()
+        else:
+            for i in range(k):
+                resident_step(i)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = lib.dmel_launch_count(-1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    resident_loop(args.steps)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches_eager = lib.dmel_launch_count(-1) - launches0
+    per_step_launches = 4   # prep + forward + backward + finalize (plus 3 driver memsets, not counted)
+    gpu_launches = per_step_launches * args.steps
+
+    # per-kernel durations: same steps, eager, each main kernel bracketed by CUDA events on its stream
+    kprof_steps = min(args.steps, 200)
+    lib.dmel_profile_enable(1)
+    for i in range(kprof_steps):
+        resident_step(i)
+    torch.cuda.synchronize(dev)
+    kern = {}
+    for kind, name in ((0, "prep"), (1, "fwd"), (2, "bwd"), (3, "finalize")):
+        tot, cnt = ctypes.c_double(), ctypes.c_longlong()
+        assert lib.dmel_profile_read(kind, ctypes.byref(tot), ctypes.byref(cnt)) == 0
+        kern[name] = (tot.value / max(cnt.value, 1), cnt.value)
+    lib.dmel_profile_enable(0)
+
+    # ---- e2e through the public module from pinned host memory ----
+    e2e = None
+    if not args.no_e2e:
+        layer = dm.MelSpectrogramLayer(torch.tensor(lam), n_mels=M, n_points=N, sample_rate=sr, hop_length=hop,
+                                       device=str(dev), optimized=True, log_eps=LOG_EPS).to(dev)
+        Rh = min(R, 4)
+        hgen = torch.Generator().manual_seed(1234 + rank)
+        host_x = [torch.randn(B, N, generator=hgen).pin_memory() for _ in range(Rh)]
+        host_out = torch.zeros(2, 2).pin_memory()
+        xdev = [torch.empty(B, N, device=dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(dev)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+        main_stream = torch.cuda.current_stream(dev)
+
+        def e2e_loop(k):
+            for i in range(k + 1):
+                if i < k:                      # upload clip batch i while batch i-1 computes
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(free[i % 2])
+                        xdev[i % 2].copy_(host_x[i % Rh], non_blocking=True)
+                        ready[i % 2].record(copy_stream)
+                if i > 0:
+                    j = i - 1
+                    main_stream.wait_event(ready[j % 2])
+                    xin = xdev[j % 2].detach().requires_grad_(True)
+                    layer.lambd.grad = None
+                    y = layer(xin)
+                    y.backward(Gs[j % R])
+                    if world > 1:
+                        dm.allreduce_lambda_grad([layer.lambd])
+                    free[j % 2].record(main_stream)
+                    # the step's scalar results go back to the host: dL/dlambda and one checksum element of dL/dx
+                    host_out[j % 2, 0].copy_(layer.lambd.grad, non_blocking=True)
+                    host_out[j % 2, 1].copy_(xin.grad[0, 0], non_blocking=True)
+
+        for e in free:
+            e.record(main_stream)
+        e2e_steps = max(10, min(args.steps, int(2.0e6 / audio_s)))
+        e2e_loop(max(3, min(args.warmup, 10)))
+        barrier()
+        ev0.record()
+        e2e_loop(e2e_steps)
+        ev1.record()
+        barrier()
+        ms_e2e = ev0.elapsed_time(ev1)
+        e2e = (ms_e2e, e2e_steps)
+
+    clocks = sampler.stop() if sampler else None
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms, e2e[0] if e2e else 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        if e2e:
+            e2e = (float(t[1]), e2e[1])
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        value = world * audio_s * args.steps / (ms * 1e-3)
+        dom = "bwd" if kern["bwd"][0] >= kern["fwd"][0] else "fwd"
+        dom_ms = kern[dom][0]
+        achieved = algorithmic_bytes(w, dom) / (dom_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
+            except Exception:
+                traffic = None
+        step_ms = ms / args.steps
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": config_dict(args, w, extra={
+                "l2_policy": f"inputs rotate over {R} buffer sets ({R * set_bytes / 2**20:.0f} MiB > 2x L2)",
+                "launch": "cuda_graph" if graph is not None else "eager",
+                "collective": "nccl all_reduce(dL/dlambda, 1 x fp32) per step" if world > 1 else "none (1 GPU)"}),
+            "gpu_launches": gpu_launches,
+            "kernels_ms": {k: round(v[0], 6) for k, v in kern.items()},
+            "roofline": {"bound": "hbm", "kernel": f"dmel_{dom}_kernel<{w['n_fft']}>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algorithmic_bytes(w, dom),
+                         "step_frac": algorithmic_bytes(w, "step") / (step_ms * 1e-3) / 1e9 / peak},
+            "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = {"value": world * audio_s * e2e[1] / (e2e[0] * 1e-3), "unit": UNIT,
+                           "h2d_bytes_per_step": 4 * B * N, "d2h_bytes_per_step": 8, "steps": e2e[1],
+                           "api": "MelSpectrogramLayer.forward + Tensor.backward, pinned host x, double-buffered H2D"}
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            rate, n, reps, _ = cpu_port_rate(w, args.cpu_budget, cores)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n} of {B} clips, best of {reps} passes, fwd+bwd (dx+dlambda), torch threads={cores}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,9 @@ EXPORTED_SYMBOLS = (
     "dmel_forward_f32",
     "dmel_backward_f32",
     "dmel_query_launch",
+    "dmel_launch_count",
+    "dmel_profile_enable",
+    "dmel_profile_read",
 )
 
 
@@ -107,6 +110,16 @@ def _declare(lib: ctypes.CDLL) -> None:
     ]
 
 
+def _declare_instrumentation(lib: ctypes.CDLL) -> None:
+    c = ctypes
+    lib.dmel_launch_count.restype = c.c_longlong
+    lib.dmel_launch_count.argtypes = [c.c_int32]
+    lib.dmel_profile_enable.restype = None
+    lib.dmel_profile_enable.argtypes = [c.c_int32]
+    lib.dmel_profile_read.restype = c.c_int
+    lib.dmel_profile_read.argtypes = [c.c_int32, c.POINTER(c.c_double), c.POINTER(c.c_longlong)]
+
+
 def load() -> ctypes.CDLL:
     """Load (once) and return the library; raises DmelError if it cannot be used."""
     global _lib
@@ -125,6 +138,7 @@ def load() -> ctypes.CDLL:
         if missing:
             raise DmelError(f"{LIB_PATH} does not export {missing}")
         _declare(lib)
+        _declare_instrumentation(lib)
         got = lib.dmel_abi_version()
         if got != ABI_VERSION:
             raise DmelError(f"libdmel_b200.so ABI version {got}, binding expects {ABI_VERSION}")

@@ -25,6 +25,9 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+#include <vector>
+
 #include "../../include/dmel.h"
 #include "fft_device.cuh"
 
@@ -676,6 +679,39 @@ static int plan_launch(int64_t N, int n_fft, int hop, int rows, bool bwd, bool n
     return DMEL_ERR_SMEM_EXCEEDED;
 }
 
+// ---- optional instrumentation for bench.py: launch counter + per-kernel CUDA-event timing.
+// Off by default; when on, every main-kernel launch is bracketed by a pair of events recorded on
+// the launching stream (no synchronisation until dmel_profile_read).
+enum { PROF_PREP = 0, PROF_FWD = 1, PROF_BWD = 2, PROF_FINALIZE = 3, PROF_KINDS = 4 };
+static std::atomic<long long> g_launches[PROF_KINDS];
+struct ProfState {
+    bool on = false;
+    std::vector<cudaEvent_t> ev[PROF_KINDS];  // start/stop pairs
+};
+static thread_local ProfState t_prof;
+
+struct ProfScope {
+    int kind;
+    cudaStream_t st;
+    ProfScope(int k, cudaStream_t s) : kind(k), st(s) {
+        g_launches[kind].fetch_add(1, std::memory_order_relaxed);
+        if (t_prof.on) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, st);
+            t_prof.ev[kind].push_back(e);
+        }
+    }
+    ~ProfScope() {
+        if (t_prof.on) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, st);
+            t_prof.ev[kind].push_back(e);
+        }
+    }
+};
+
 static int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -703,6 +739,7 @@ static int launch_fwd(const float* x, float* y, const Geom& g, const MelDev& mel
                       const LaunchPlan& lp, cudaStream_t st) {
     const unsigned grid = unsigned(int64_t(g.B) * g.tiles_per_clip);
     int rc;
+    ProfScope prof(PROF_FWD, st);
     if (spec) {
         if ((rc = set_smem(dmel_fwd_kernel<L, true>, lp.smem))) return rc;
         dmel_fwd_kernel<L, true><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means);
@@ -719,6 +756,7 @@ static int launch_bwd_t(const float* x, const float* y, const float* gy, float* 
     const unsigned grid = unsigned(int64_t(g.B) * g.tiles_per_clip);
     int rc;
     if ((rc = set_smem(dmel_bwd_kernel<L, SPEC, NEED_DX>, lp.smem))) return rc;
+    ProfScope prof(PROF_BWD, st);
     dmel_bwd_kernel<L, SPEC, NEED_DX>
         <<<grid, lp.threads, lp.smem, st>>>(x, y, gy, dx, g, mel, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
     return check_launch("dmel_bwd_kernel");
@@ -772,6 +810,7 @@ static MelDev mel_dev(const dmel_melbank* bank) {
 
 static int run_prep(const float* x, int64_t B, int64_t N, int64_t stride, float lam_abs, int32_t win, int32_t n_fft,
                     int32_t flags, const WsView& ws, cudaStream_t st) {
+    ProfScope prof(PROF_PREP, st);
     dmel_prep_kernel<<<unsigned(B + 1), PREP_THREADS, 0, st>>>(x, stride, int(B), int(N), lam_abs, win, n_fft,
                                                                 flags, ws);
     return check_launch("dmel_prep_kernel");
@@ -873,6 +912,7 @@ extern "C" DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t 
     const MelDev mel = mel_dev(bank);
     if (lp.path == 1) {
         if ((rc = set_smem(dmel_dft_kernel<false, false>, lp.smem))) return rc;
+        ProfScope prof(PROF_FWD, st);
         dmel_dft_kernel<false, false><<<unsigned(int64_t(g.B) * g.T), DFT_THREADS, lp.smem, st>>>(
             x, nullptr, nullptr, y, nullptr, g, mel, spec ? 1 : 0, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
         return check_launch("dmel_dft_kernel<fwd>");
@@ -916,6 +956,7 @@ extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t
     const MelDev mel = mel_dev(bank);
     if (lp.path == 1) {
         const unsigned grid = unsigned(int64_t(g.B) * g.T);
+        ProfScope prof(PROF_BWD, st);
         if (need_dx) {
             if ((rc = set_smem(dmel_dft_kernel<true, true>, lp.smem))) return rc;
             dmel_dft_kernel<true, true><<<grid, DFT_THREADS, lp.smem, st>>>(
@@ -940,7 +981,40 @@ extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t
     }
     const double* csum = (flags & DMEL_FLAG_KEEP_MEAN) ? nullptr : ws.clipsum;
     if (!csum) grid = 1;
+    ProfScope prof(PROF_FINALIZE, st);
     dmel_finalize_kernel<<<unsigned(grid), 256, 0, st>>>(grad_x, int(batch), int(n_points), chunks, csum, ws.hdr,
                                                          sign, grad_lambda);
     return check_launch("dmel_finalize_kernel");
+}
+
+extern "C" DMEL_API long long dmel_launch_count(int32_t kind) {
+    if (kind < 0) {
+        long long t = 0;
+        for (int k = 0; k < PROF_KINDS; ++k) t += g_launches[k].load(std::memory_order_relaxed);
+        return t;
+    }
+    return kind < PROF_KINDS ? g_launches[kind].load(std::memory_order_relaxed) : 0;
+}
+
+extern "C" DMEL_API void dmel_profile_enable(int32_t on) {
+    for (int k = 0; k < PROF_KINDS; ++k) {
+        for (cudaEvent_t e : t_prof.ev[k]) cudaEventDestroy(e);
+        t_prof.ev[k].clear();
+    }
+    t_prof.on = on != 0;
+}
+
+extern "C" DMEL_API int dmel_profile_read(int32_t kind, double* total_ms, long long* launches) {
+    if (kind < 0 || kind >= PROF_KINDS || !total_ms || !launches) return DMEL_ERR_BAD_GEOMETRY;
+    double tot = 0.0;
+    const std::vector<cudaEvent_t>& v = t_prof.ev[kind];
+    for (size_t i = 0; i + 1 < v.size(); i += 2) {
+        if (cudaEventSynchronize(v[i + 1]) != cudaSuccess) return DMEL_ERR_LAUNCH_FAILED;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, v[i], v[i + 1]) != cudaSuccess) return DMEL_ERR_LAUNCH_FAILED;
+        tot += ms;
+    }
+    *total_ms = tot;
+    *launches = (long long)(v.size() / 2);
+    return DMEL_OK;
 }

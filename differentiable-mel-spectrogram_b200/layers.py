@@ -21,6 +21,24 @@ from . import _lib
 from .op import dmel
 
 
+class _LambdaMirror:
+    """Host copy of `lambd`, refreshed only when the parameter was written (optimizer.step(), fill_,
+    load_state_dict all bump the tensor's version counter).  Removes the device->host sync that picks
+    n_fft from every forward whose lambda did not change (validation loops, frozen layers, benchmarks);
+    the reference pays that sync once per sample (time_frequency.py:39)."""
+
+    def __init__(self):
+        self._key = None
+        self._value = 0.0
+
+    def get(self, lambd: torch.Tensor) -> float:
+        key = (lambd._version, lambd.data_ptr(), lambd.device)
+        if key != self._key:
+            self._value = float(lambd.detach().to(torch.float32).item())
+            self._key = key
+        return self._value
+
+
 def _resolve_device(module_device, lambd: torch.Tensor) -> torch.device:
     # The reference keeps a `device` attribute and also follows `net.to(device)` (main.py:25).
     # The parameter's device is the truth once the module has been moved.
@@ -45,6 +63,7 @@ class MelSpectrogramLayer(nn.Module):
         self.n_freq = n_mels
         self.n_time = n_points // hop_length + 1
         self.log_eps = log_eps
+        self._mirror = _LambdaMirror()
 
     def forward(self, x):
         dev = _resolve_device(self.device, self.lambd)
@@ -61,7 +80,8 @@ class MelSpectrogramLayer(nn.Module):
                                f"layer was built for n_time={self.n_time}")
         return dmel(x, self.lambd, hop_length=self.hop_length, optimized=self.optimized,
                     normalize_window=self.normalize_window, n_mels=self.n_mels, sample_rate=self.sample_rate,
-                    f_min=self.f_min, f_max=self.f_max, log_eps=self.log_eps)
+                    f_min=self.f_min, f_max=self.f_max, log_eps=self.log_eps,
+                    lambd_value=self._mirror.get(self.lambd))
 
     def extra_repr(self):
         return (f"n_mels={self.n_mels}, sample_rate={self.sample_rate}, hop_length={self.hop_length}, "
@@ -79,6 +99,7 @@ class SpectrogramLayer(nn.Module):
         self.optimized = optimized
         self.normalize_window = normalize_window
         self.log_eps = log_eps
+        self._mirror = _LambdaMirror()
 
     def forward(self, x):
         dev = _resolve_device(self.device, self.lambd)
@@ -89,7 +110,8 @@ class SpectrogramLayer(nn.Module):
         if x.device != dev:
             x = x.to(dev, non_blocking=True)
         s = dmel(x, self.lambd, hop_length=self.hop_length, optimized=self.optimized,
-                 normalize_window=self.normalize_window, n_mels=0, log_eps=self.log_eps)
+                 normalize_window=self.normalize_window, n_mels=0, log_eps=self.log_eps,
+                 lambd_value=self._mirror.get(self.lambd))
         if self.optimized and tuple(s.shape[2:]) != tuple(self.size):
             # models.py:186,198: the reference allocates `size` and assigns the (F, T) spectrogram into it
             raise RuntimeError(f"spectrogram of shape {tuple(s.shape[2:])} does not fit size={tuple(self.size)}")

@@ -137,14 +137,16 @@ class DmelFunction(torch.autograd.Function):
 
 def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bool,
          normalize_window: bool = False, n_mels: int = 0, sample_rate: int = 0, f_min: float = 0.0,
-         f_max: Optional[float] = None, log_eps: Optional[float] = None, remove_mean: bool = True) -> torch.Tensor:
+         f_max: Optional[float] = None, log_eps: Optional[float] = None, remove_mean: bool = True,
+         lambd_value: Optional[float] = None) -> torch.Tensor:
     """Functional form of both layers.
 
     x: (B, N) CUDA tensor (fp32; fp64/fp16 inputs are cast to fp32 — the reference's fp64
     synthetic dataset ends in an fp32 output buffer anyway, models.py:189).  Returns
     (B, 1, rows, N//hop + 1) fp32, contiguous: the linear (mel) power spectrogram, or its
     log(. + log_eps) when log_eps is given (the classifiers' energy_normalize, models.py:72).
-    n_mels == 0 selects spectrogram mode (models.py:171-200).
+    n_mels == 0 selects spectrogram mode (models.py:171-200).  `lambd_value`, if given, must equal
+    lambd's current value (it only saves the device->host read that picks n_fft).
     """
     if x.dim() != 2:
         raise ValueError(f"expected x of shape (batch, n_points), got {tuple(x.shape)}")
@@ -157,8 +159,9 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
         x = x.contiguous()
     if lambd.device != x.device:
         raise _lib.DmelError(f"lambd on {lambd.device} but x on {x.device}")
-    # the one host sync of the forward (the reference syncs once per sample)
-    lam_value = float(lambd.detach().to(torch.float32).item())
+    # the one host sync of the forward (the reference syncs once per sample); callers that keep a
+    # host mirror of lambd (the layers do, keyed on the parameter's version counter) pass it in
+    lam_value = float(lambd.detach().to(torch.float32).item()) if lambd_value is None else float(lambd_value)
     B, N = x.shape
     geo = resolve_geometry(B, N, hop_length, lam_value, optimized, n_mels)
     lib = _lib.load()

@@ -130,6 +130,14 @@ DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t n_points, 
 DMEL_API int dmel_query_launch(int64_t n_points, int32_t n_fft, int32_t hop, int32_t rows, int32_t which,
                       int32_t* tile_frames, int32_t* smem_bytes, int32_t* threads, int32_t* path);
 
+/* Instrumentation (bench.py): cumulative number of kernels this library launched, by kind
+ * (0 prep, 1 forward, 2 backward, 3 finalize, <0 all); and opt-in per-launch CUDA-event timing of
+ * the calling thread's launches: enable(1) clears and starts, read() synchronises on the recorded
+ * events and returns their summed duration and count, enable(0) stops and frees the events.      */
+DMEL_API long long dmel_launch_count(int32_t kind);
+DMEL_API void dmel_profile_enable(int32_t on);
+DMEL_API int dmel_profile_read(int32_t kind, double* total_ms, long long* launches);
+
 #define DMEL_MAX_DFT_NFFT 32768
 
 #ifdef __cplusplus

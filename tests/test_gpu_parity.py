@@ -134,18 +134,18 @@ def test_full_size_properties_esc50_and_large_batch(cuda_device):
         x = torch.randn(B, N, generator=g).to(dev)
         ll = torch.tensor(lam, device=dev, requires_grad=True)
         kw = dict(hop_length=hop, optimized=True, n_mels=M, sample_rate=sr)
-        y = dm.dmel(x, ll, **kw)
+        y = dm.dmel(x, ll, **kw).detach()
         assert y.shape == (B, 1, M, N // hop + 1) and y.is_contiguous() and torch.isfinite(y).all()
         # (a) clips are independent: permuting the batch permutes the output bit-exactly
         perm = torch.randperm(B, generator=g).to(dev)
-        assert torch.equal(dm.dmel(x[perm], ll, **kw), y[perm])
+        assert torch.equal(dm.dmel(x[perm], ll, **kw).detach(), y[perm])
         # (b) sharding the batch (what the multi-GPU path does) changes nothing, bit for bit
         h = B // 2
-        assert torch.equal(torch.cat([dm.dmel(x[:h], ll, **kw), dm.dmel(x[h:], ll, **kw)]), y)
+        assert torch.equal(torch.cat([dm.dmel(x[:h], ll, **kw), dm.dmel(x[h:], ll, **kw)]).detach(), y)
         # (c) power is quadratic: scaling by 2 scales every output by exactly 4 in fp32; DC offset is removed
-        assert torch.equal(dm.dmel(2.0 * x, ll, **kw), 4.0 * y)
+        assert torch.equal(dm.dmel(2.0 * x, ll, **kw).detach(), 4.0 * y)
         y_dc = dm.dmel(x + 3.0, ll, **kw)
-        assert rel_err(y_dc.cpu().numpy(), y.cpu().numpy()) < 1e-4
+        assert rel_err(y_dc.detach().cpu().numpy(), y.detach().cpu().numpy()) < 1e-4
         # (d) d/dlambda accumulated over shards equals the whole-batch gradient; dx rows have zero mean
         G = torch.randn(y.shape, generator=torch.Generator().manual_seed(9)).to(dev)
         xx = x.clone().requires_grad_(True)
@@ -163,6 +163,7 @@ def test_full_size_properties_esc50_and_large_batch(cuda_device):
                                          optimized=True, n_mels=M, sample_rate=sr)
         check_y(yl[sub].detach().cpu().numpy(), want[0], False)
         assert rel_err(dx[sub].cpu().numpy(), want[1]) < G_RTOL
+        ll.grad = None
         del x, y, G, xx, yl, dx
         torch.cuda.empty_cache()
 
