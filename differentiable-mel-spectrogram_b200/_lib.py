@@ -39,6 +39,8 @@ class MelBankStruct(ctypes.Structure):
     _fields_ = [
         ("n_freqs", ctypes.c_int32),
         ("n_mels", ctypes.c_int32),
+        ("mel_nnz", ctypes.c_int32),
+        ("bin_nnz", ctypes.c_int32),
         ("mel_k0", ctypes.c_void_p),
         ("mel_off", ctypes.c_void_p),
         ("mel_w", ctypes.c_void_p),
@@ -105,8 +107,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     ]
     lib.dmel_query_launch.restype = c.c_int
     lib.dmel_query_launch.argtypes = [
-        c.c_int64, c.c_int32, c.c_int32, c.c_int32, c.c_int32,
-        c.POINTER(c.c_int32), c.POINTER(c.c_int32), c.POINTER(c.c_int32), c.POINTER(c.c_int32),
+        c.c_int64, c.c_int64, c.c_int32, c.c_int32, c.c_int32, c.c_int32, c.c_int32,
+        c.POINTER(c.c_int32), c.POINTER(c.c_int32), c.POINTER(c.c_int32), c.POINTER(c.c_int32), c.POINTER(c.c_int32),
     ]
 
 

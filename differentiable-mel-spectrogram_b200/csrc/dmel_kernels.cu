@@ -10,12 +10,15 @@
 //                         centre-padded to n_fft like torch.stft does), twiddle table, scalars
 //   dmel_fwd_kernel<L>    one CTA = one tile of TT frames of one clip: the clip span is staged
 //                         once in shared memory (mean removed, zero padded = center=True,
-//                         pad_mode='constant'); frames are transformed two at a time as the
-//                         real/imag parts of one L-point complex FFT; |X|^2, the sparse mel
-//                         gather and the log happen on chip; only y is written
-//   dmel_bwd_kernel<L>    recomputes the frames' spectra, forms Z = 2*GP*X, inverse-transforms
-//                         two frames at a time, overlap-adds u*w into a shared-memory dx span and
-//                         accumulates dL/dlambda = sum u*fr*dw/dlambda in registers
+//                         pad_mode='constant') next to the window, the twiddle tables and the
+//                         sparse filterbank.  NG independent FFT groups (one warp each for
+//                         L <= 512) split the tile into contiguous sub-tiles and transform their
+//                         frames two at a time as the real/imag parts of one L-point complex FFT;
+//                         |X|^2, the sparse mel gather and the log happen on chip; only y is written
+//   dmel_bwd_kernel<L>    same decomposition: recomputes the spectra, forms Z = 2*GP*X, inverse-
+//                         transforms two frames at a time, overlap-adds u*w into the group's private
+//                         shared-memory dx sub-span (merged per tile at the end) and accumulates
+//                         dL/dlambda = sum u*fr*dw/dlambda in registers
 //   dmel_finalize_kernel  dx -= mean(dx) per clip (adjoint of the mean removal), fp64 -> fp32
 //                         dL/dlambda with sign(lambda) (adjoint of torch.abs, models.py:38)
 //   dmel_dft_*            direct-DFT versions of fwd/bwd for transform lengths without an FFT
@@ -25,7 +28,11 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <stdlib.h>
+
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <vector>
 
 #include "../../include/dmel.h"
@@ -79,7 +86,11 @@ static WsView ws_view(void* base, int64_t B, int32_t n_fft) {
 
 struct Geom {
     int B, N, T, hop, n_fft, M;  // M = output rows (n_mels, or n_fft/2+1 in spectrogram mode)
-    int TT, tiles_per_clip, span;
+    int TT;                      // frames per CTA tile (= NG * SF)
+    int SF;                      // frames per group sub-tile (even)
+    int tiles_per_clip, span;    // span = (TT-1)*hop + n_fft samples staged per tile
+    int sub_span;                // (SF-1)*hop + n_fft: private dx span of one group
+    int csr_ints, csr_floats;    // size of the sparse-bank form the kernel stages (0 in spectrogram mode)
     long long x_stride;
     float log_eps;
 };
@@ -122,9 +133,15 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // ----------------------------------------------------------------------------
 constexpr int PREP_THREADS = 256;
 
+// host mirror of fft_device.cuh's Plan<L> (np == 0: no FFT plan, direct-DFT path)
+struct PlanDesc {
+    int np;
+    int r[4];
+};
+
 __global__ void __launch_bounds__(PREP_THREADS)
 dmel_prep_kernel(const float* __restrict__ x, long long x_stride, int B, int N, float lam_abs, int win_length,
-                 int n_fft, int flags, WsView ws) {
+                 int n_fft, int flags, WsView ws, PlanDesc plan) {
     __shared__ double red[32];
     const int tid = threadIdx.x;
     const int normalize = flags & DMEL_FLAG_NORMALIZE_WINDOW;
@@ -165,9 +182,26 @@ dmel_prep_kernel(const float* __restrict__ x, long long x_stride, int B, int N, 
             sq += double(w) * double(w) * double(d * d * inv_lam3);
         }
         ws.win[n] = w;
-        double sn, cs;
-        sincospi(-2.0 * double(n) / double(n_fft), &sn, &cs);
-        ws.tw[n] = make_float2(float(cs), float(sn));
+        if (plan.np == 0) {  // direct-DFT path: plain table exp(-2*pi*i*n/n_fft)
+            double sn, cs;
+            sincospi(-2.0 * double(n) / double(n_fft), &sn, &cs);
+            ws.tw[n] = make_float2(float(cs), float(sn));
+        }
+    }
+    // FFT path: per-pass tables T_p[r-1][k] = exp(-2*pi*i*k*r/(NS_p*R_p)) (fft_device.cuh, TwOffset)
+    {
+        int off = 0, ns = plan.r[0];
+        for (int p = 1; p < plan.np; ++p) {
+            const int R = plan.r[p], cnt = (R - 1) * ns;
+            for (int e = tid; e < cnt; e += PREP_THREADS) {
+                const int r = e / ns + 1, k = e - (r - 1) * ns;
+                double sn, cs;
+                sincospi(-2.0 * double(k) * double(r) / (double(ns) * double(R)), &sn, &cs);
+                ws.tw[off + e] = make_float2(float(cs), float(sn));
+            }
+            off += cnt;
+            ns *= R;
+        }
     }
     const double S2 = block_sum(s2, red);
     __shared__ float sh_scale;
@@ -195,43 +229,68 @@ dmel_prep_kernel(const float* __restrict__ x, long long x_stride, int B, int N, 
 }
 
 // ----------------------------------------------------------------------------
-// shared-memory carve-up shared by host and device
+// shared-memory carve-up shared by host and device (offsets in 4-byte words, all multiples of 4)
 // ----------------------------------------------------------------------------
 __host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
 
-// bytes: [buf0 L*8][buf1 L*8][win L*4][xs span4*4][dxs span4*4 (bwd+dx)][tile M*(TT+1)*4][red 256]
-static size_t smem_bytes_fft(int L, int span, int M, int TT, bool need_dxs) {
-    size_t s = size_t(L) * 16 + size_t(L) * 4;
-    s += size_t(round_up4(span)) * 4 * (need_dxs ? 2 : 1);
-    s += size_t(round_up4(M * (TT + 1))) * 4;
-    s += 256;
-    return s;
+struct SmemLay {
+    int twt, win, xs, tile, csr_i, csr_w, red, grp, grp_stride, total;
+};
+
+__host__ __device__ inline SmemLay make_lay(int L, int NG, int tw_total, int span, int sub_span, int tile_words,
+                                            int csr_ints, int csr_floats, bool priv_dx) {
+    SmemLay l;
+    int o = 0;
+    l.twt = o;   o += round_up4(2 * tw_total);
+    l.win = o;   o += L;
+    l.xs = o;    o += round_up4(span);
+    l.tile = o;  o += round_up4(tile_words);
+    l.csr_i = o; o += round_up4(csr_ints);
+    l.csr_w = o; o += round_up4(csr_floats);
+    l.red = o;   o += 64;
+    l.grp = o;
+    l.grp_stride = 2 * L + (priv_dx ? round_up4(sub_span) : 0);
+    o += NG * l.grp_stride;
+    l.total = o;
+    return l;
 }
 
 // ----------------------------------------------------------------------------
 // forward
 // ----------------------------------------------------------------------------
-template <int L, bool SPEC>
-__global__ void __launch_bounds__(L / Plan<L>::E)
+template <int L, int NG, bool SPEC>
+__global__ void __launch_bounds__(NG * (L / Plan<L>::E))
 dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelDev mel,
-                const float* __restrict__ win_g, const float2* __restrict__ tw, const float* __restrict__ means) {
-    constexpr int E = Plan<L>::E, NT = L / E;
+                const float* __restrict__ win_g, const float2* __restrict__ tw_g, const float* __restrict__ means) {
+    constexpr int E = Plan<L>::E, GT = L / E, NT = NG * GT, TWN = TwTotal<L>::value;
     using P0 = Pass<L, 0>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* buf0 = reinterpret_cast<float2*>(smem_raw);
-    float2* buf1 = buf0 + L;
-    float* win = reinterpret_cast<float*>(buf1 + L);
-    float* xs = win + L;
-    float* tile = xs + round_up4(g.span);
+    extern __shared__ __align__(16) float smem_f[];
+    const int TS = g.TT + 1;
+    const SmemLay lay = make_lay(L, NG, TWN, g.span, g.sub_span, g.M * TS, g.csr_ints, g.csr_floats, false);
+    float2* twt = reinterpret_cast<float2*>(smem_f + lay.twt);
+    float* win = smem_f + lay.win;
+    float* xs = smem_f + lay.xs;
+    float* tile = smem_f + lay.tile;
+    int* csr_i = reinterpret_cast<int*>(smem_f + lay.csr_i);
+    float* csr_w = smem_f + lay.csr_w;
 
     const int tid = threadIdx.x;
+    const int grp = tid / GT, gtid = tid - grp * GT, bar_id = 1 + grp;
+    float2* buf = reinterpret_cast<float2*>(smem_f + lay.grp + grp * lay.grp_stride);
     const int b = blockIdx.x / g.tiles_per_clip;
     const int tile_i = blockIdx.x - b * g.tiles_per_clip;
     const int t0 = tile_i * g.TT;
     const int nfr = min(g.TT, g.T - t0);
-    const int TS = g.TT + 1;
 
+    // stage everything the tile needs, once
+    for (int i = tid; i < TWN; i += NT) twt[i] = __ldg(tw_g + i);
     for (int i = tid; i < L; i += NT) win[i] = __ldg(win_g + i);
+    if (!SPEC) {
+        // mel-major sparse bank: ints = k0[M] | off[M+1], floats = weights
+        for (int i = tid; i < g.M; i += NT) csr_i[i] = __ldg(mel.mel_k0 + i);
+        for (int i = tid; i <= g.M; i += NT) csr_i[g.M + i] = __ldg(mel.mel_off + i);
+        for (int i = tid; i < g.csr_floats; i += NT) csr_w[i] = __ldg(mel.mel_w + i);
+    }
     {
         const float mu = __ldg(means + b);
         const float* xb = x + (long long)b * g.x_stride;
@@ -243,14 +302,14 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
     }
     __syncthreads();
 
-    int sel = 0;
-    for (int f = 0; f < nfr; f += 2) {
+    const int f_hi = min(grp * g.SF + g.SF, nfr);
+    for (int f = grp * g.SF; f < f_hi; f += 2) {
         const float* xa = xs + f * g.hop;
         const float* xb2 = xa + g.hop;
         float2 v[E];
 #pragma unroll
         for (int i = 0; i < P0::NB; ++i) {
-            const int j = tid + i * NT;
+            const int j = gtid + i * GT;
 #pragma unroll
             for (int r = 0; r < P0::R; ++r) {
                 const int n = j + r * P0::STR;
@@ -258,12 +317,11 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
                 v[i * P0::R + r] = make_float2(xa[n] * w, xb2[n] * w);
             }
         }
-        run_passes<L, 0, true>(v, buf0, buf1, sel, tw, tid);
-        float2* Z = sel ? buf0 : buf1;  // buffer written last
-        // packed pair -> two one-sided power spectra (time_frequency.py:53)
-        for (int k = tid; k <= L / 2; k += NT) {
-            const float2 z1 = Z[k];
-            const float2 z2 = Z[(L - k) & (L - 1)];
+        run_passes<L, 0, true>(v, buf, twt, gtid, bar_id);
+        // packed pair -> two one-sided power spectra (time_frequency.py:53), in place
+        for (int k = gtid; k <= L / 2; k += GT) {
+            const float2 z1 = buf[k];
+            const float2 z2 = buf[(L - k) & (L - 1)];
             const float ar = 0.5f * (z1.x + z2.x), ai = 0.5f * (z1.y - z2.y);
             const float br = 0.5f * (z1.y + z2.y), bi = 0.5f * (z2.x - z1.x);
             const float pa = fmaf(ar, ar, ai * ai), pb = fmaf(br, br, bi * bi);
@@ -271,19 +329,19 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
                 tile[k * TS + f] = pa;
                 tile[k * TS + f + 1] = pb;
             } else {
-                Z[k] = make_float2(pa, pb);
+                buf[k] = make_float2(pa, pb);
             }
         }
         if (!SPEC) {
-            __syncthreads();
+            group_sync<GT>(bar_id);
             // models.py:53 matmul(spec^T, mel_fb): each mel reads its contiguous run of bins
-            for (int m = tid; m < g.M; m += NT) {
-                const int k0 = __ldg(mel.mel_k0 + m);
-                const int o0 = __ldg(mel.mel_off + m), o1 = __ldg(mel.mel_off + m + 1);
+            for (int m = gtid; m < g.M; m += GT) {
+                const int k0 = csr_i[m];
+                const int o0 = csr_i[g.M + m], o1 = csr_i[g.M + m + 1];
                 float sa = 0.f, sb = 0.f;
                 for (int o = o0; o < o1; ++o) {
-                    const float w = __ldg(mel.mel_w + o);
-                    const float2 p = Z[k0 + (o - o0)];
+                    const float w = csr_w[o];
+                    const float2 p = buf[k0 + (o - o0)];
                     sa = fmaf(w, p.x, sa);
                     sb = fmaf(w, p.y, sb);
                 }
@@ -307,42 +365,55 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
 // ----------------------------------------------------------------------------
 // backward
 // ----------------------------------------------------------------------------
-template <int L, bool SPEC, bool NEED_DX>
-__global__ void __launch_bounds__(L / Plan<L>::E)
+template <int L, int NG, bool SPEC, bool NEED_DX>
+__global__ void __launch_bounds__(NG * (L / Plan<L>::E))
 dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy,
                 float* __restrict__ dx, Geom g, MelDev mel, const float* __restrict__ win_g,
-                const float2* __restrict__ tw, const float* __restrict__ means, WsHeader* hdr,
+                const float2* __restrict__ tw_g, const float* __restrict__ means, WsHeader* hdr,
                 double* __restrict__ clipsum) {
-    constexpr int E = Plan<L>::E, NT = L / E, NP = Plan<L>::NP;
+    constexpr int E = Plan<L>::E, GT = L / E, NT = NG * GT, NP = Plan<L>::NP, TWN = TwTotal<L>::value;
+    constexpr int F = L / 2 + 1;
     using P0 = Pass<L, 0>;
     using PL = Pass<L, NP - 1>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* buf0 = reinterpret_cast<float2*>(smem_raw);
-    float2* buf1 = buf0 + L;
-    float* win = reinterpret_cast<float*>(buf1 + L);
-    float* xs = win + L;
-    float* dxs = xs + round_up4(g.span);
-    float* gt = NEED_DX ? dxs + round_up4(g.span) : dxs;
-    double* red = reinterpret_cast<double*>(gt + round_up4(g.M * (g.TT + 1)));
+    extern __shared__ __align__(16) float smem_f[];
+    const int TS = g.TT + 1;
+    const SmemLay lay = make_lay(L, NG, TWN, g.span, g.sub_span, g.M * TS, g.csr_ints, g.csr_floats, NEED_DX);
+    float2* twt = reinterpret_cast<float2*>(smem_f + lay.twt);
+    float* win = smem_f + lay.win;
+    float* xs = smem_f + lay.xs;
+    float* gt = smem_f + lay.tile;
+    int* csr_i = reinterpret_cast<int*>(smem_f + lay.csr_i);
+    float* csr_w = smem_f + lay.csr_w;
+    double* red = reinterpret_cast<double*>(smem_f + lay.red);
 
     const int tid = threadIdx.x;
+    const int grp = tid / GT, gtid = tid - grp * GT, bar_id = 1 + grp;
+    float2* buf = reinterpret_cast<float2*>(smem_f + lay.grp + grp * lay.grp_stride);
+    float* priv = smem_f + lay.grp + grp * lay.grp_stride + 2 * L;   // this group's dx sub-span
     const int b = blockIdx.x / g.tiles_per_clip;
     const int tile_i = blockIdx.x - b * g.tiles_per_clip;
     const int t0 = tile_i * g.TT;
     const int nfr = min(g.TT, g.T - t0);
-    const int TS = g.TT + 1;
     const int p0 = t0 * g.hop - L / 2;
 
+    for (int i = tid; i < TWN; i += NT) twt[i] = __ldg(tw_g + i);
     for (int i = tid; i < L; i += NT) win[i] = __ldg(win_g + i);
+    if (!SPEC) {
+        // bin-major sparse bank: ints = m0[F] | off[F+1], floats = weights
+        for (int i = tid; i < F; i += NT) csr_i[i] = __ldg(mel.bin_m0 + i);
+        for (int i = tid; i <= F; i += NT) csr_i[F + i] = __ldg(mel.bin_off + i);
+        for (int i = tid; i < g.csr_floats; i += NT) csr_w[i] = __ldg(mel.bin_w + i);
+    }
     {
         const float mu = __ldg(means + b);
         const float* xb = x + (long long)b * g.x_stride;
         for (int i = tid; i < g.span; i += NT) {
             const int p = p0 + i;
             xs[i] = (p >= 0 && p < g.N) ? __ldg(xb + p) - mu : 0.f;
-            if (NEED_DX) dxs[i] = 0.f;
         }
     }
+    if (NEED_DX)
+        for (int i = gtid; i < g.sub_span; i += GT) priv[i] = 0.f;
     {
         // upstream gradient tile; with the fused log dL/dmel = G / (mel + eps) = G * exp(-y)
         const bool do_log = g.log_eps >= 0.f;
@@ -362,15 +433,16 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
 
     const float inv_lam3 = hdr->inv_lam3, cprime = hdr->cprime, centre = hdr->centre;
     float dlam = 0.f;
-    int sel = 0;
-    for (int f = 0; f < nfr; f += 2) {
+    const int f_lo = grp * g.SF;
+    const int f_hi = min(f_lo + g.SF, nfr);
+    for (int f = f_lo; f < f_hi; f += 2) {
         const float* xa = xs + f * g.hop;
         const float* xb2 = xa + g.hop;
         const bool has_b = (f + 1) < nfr;
         float2 v[E];
 #pragma unroll
         for (int i = 0; i < P0::NB; ++i) {
-            const int j = tid + i * NT;
+            const int j = gtid + i * GT;
 #pragma unroll
             for (int r = 0; r < P0::R; ++r) {
                 const int n = j + r * P0::STR;
@@ -378,12 +450,11 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
                 v[i * P0::R + r] = make_float2(xa[n] * w, xb2[n] * w);
             }
         }
-        run_passes<L, 0, true>(v, buf0, buf1, sel, tw, tid);
-        float2* Z = sel ? buf0 : buf1;
-        // Z <- conj(V),  V = Zhat_a + i*Zhat_b the Hermitian-extended 2*GP*X of both frames
-        for (int k = tid; k <= L / 2; k += NT) {
-            const float2 z1 = Z[k];
-            const float2 z2 = Z[(L - k) & (L - 1)];
+        run_passes<L, 0, true>(v, buf, twt, gtid, bar_id);
+        // buf <- conj(V),  V = Zhat_a + i*Zhat_b the Hermitian-extended 2*GP*X of both frames
+        for (int k = gtid; k <= L / 2; k += GT) {
+            const float2 z1 = buf[k];
+            const float2 z2 = buf[(L - k) & (L - 1)];
             const float ar = 0.5f * (z1.x + z2.x), ai = 0.5f * (z1.y - z2.y);
             const float br = 0.5f * (z1.y + z2.y), bi = 0.5f * (z2.x - z1.x);
             float ga = 0.f, gb = 0.f;
@@ -391,75 +462,84 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
                 ga = gt[k * TS + f];
                 gb = gt[k * TS + f + 1];
             } else {
-                const int m0 = __ldg(mel.bin_m0 + k);
-                const int o0 = __ldg(mel.bin_off + k), o1 = __ldg(mel.bin_off + k + 1);
+                const int m0 = csr_i[k];
+                const int o0 = csr_i[F + k], o1 = csr_i[F + k + 1];
                 for (int o = o0; o < o1; ++o) {
-                    const float w = __ldg(mel.bin_w + o);
+                    const float w = csr_w[o];
                     const float* gp = gt + (m0 + (o - o0)) * TS + f;
                     ga = fmaf(w, gp[0], ga);
                     gb = fmaf(w, gp[1], gb);
                 }
             }
             if (k == 0 || k == L / 2) {
-                Z[k] = make_float2(2.f * ga * ar, -2.f * gb * br);
+                buf[k] = make_float2(2.f * ga * ar, -2.f * gb * br);
             } else {
-                Z[k] = make_float2(ga * ar - gb * bi, -(ga * ai + gb * br));
-                Z[L - k] = make_float2(ga * ar + gb * bi, ga * ai - gb * br);
+                buf[k] = make_float2(ga * ar - gb * bi, -(ga * ai + gb * br));
+                buf[L - k] = make_float2(ga * ar + gb * bi, ga * ai - gb * br);
             }
         }
-        __syncthreads();
+        group_sync<GT>(bar_id);
         // inverse transform as conj(FFT(conj(V))): u_a = Re, u_b = -Im of the FFT output
-        P0::gather(v, Z, tid);
-        run_passes<L, 0, false>(v, buf0, buf1, sel, tw, tid);
+        P0::gather(v, buf, gtid);
+        run_passes<L, 0, false>(v, buf, twt, gtid, bar_id);
         // dL/dlambda, time-domain form: sum_n u[n] * fr[n] * dw/dlambda[n],
         //   dw/dlambda[n] = w[n] * ((n-centre)^2/lambda^3 - cprime)
 #pragma unroll
         for (int i = 0; i < PL::NB; ++i) {
 #pragma unroll
             for (int r = 0; r < PL::R; ++r) {
-                const int n = PL::out_index(tid, i, r);
+                const int n = PL::out_index(gtid, i, r);
                 const float2 u = v[i * PL::R + r];
                 const float w = win[n];
                 const float d = float(n) - centre;
                 const float q = fmaf(d * d, inv_lam3, -cprime);
-                const float s = u.x * xa[n] - (has_b ? u.y * xb2[n] : 0.f);
-                dlam = fmaf(w * q, s, dlam);
+                const float sdot = u.x * xa[n] - (has_b ? u.y * xb2[n] : 0.f);
+                dlam = fmaf(w * q, sdot, dlam);
                 v[i * PL::R + r] = make_float2(u.x * w, -u.y * w);
             }
         }
         if (NEED_DX) {
-            // overlap-add (adjoint of the framing): frame a, barrier, frame b, barrier
-            float* da = dxs + f * g.hop;
+            // overlap-add (adjoint of the framing) into the group's private span:
+            // frame a, barrier, frame b, barrier — no shared-memory atomics
+            float* da = priv + (f - f_lo) * g.hop;
 #pragma unroll
             for (int i = 0; i < PL::NB; ++i)
 #pragma unroll
-                for (int r = 0; r < PL::R; ++r) da[PL::out_index(tid, i, r)] += v[i * PL::R + r].x;
-            __syncthreads();
+                for (int r = 0; r < PL::R; ++r) da[PL::out_index(gtid, i, r)] += v[i * PL::R + r].x;
+            group_sync<GT>(bar_id);
             if (has_b) {
                 float* db = da + g.hop;
 #pragma unroll
                 for (int i = 0; i < PL::NB; ++i)
 #pragma unroll
-                    for (int r = 0; r < PL::R; ++r) db[PL::out_index(tid, i, r)] += v[i * PL::R + r].y;
+                    for (int r = 0; r < PL::R; ++r) db[PL::out_index(gtid, i, r)] += v[i * PL::R + r].y;
             }
-            __syncthreads();
+            group_sync<GT>(bar_id);
         }
     }
 
-    const double tot = block_sum(double(dlam), red);
+    const double tot = block_sum(double(dlam), red);   // contains __syncthreads: private spans are complete
     if (tid == 0) atomicAdd(&hdr->dlam_acc, tot);
 
     if (NEED_DX) {
-        // crop the centre padding; positions no other tile touches are stored, halos are reduced
+        // merge the groups' sub-spans; crop the centre padding; positions no other tile touches are
+        // stored, the halos shared with the neighbouring tiles are reduced into the zeroed dx
         const int span_used = (nfr - 1) * g.hop + L;
         const int excl_lo = (tile_i == 0) ? 0 : (t0 - 1) * g.hop + L / 2;
         const int excl_hi = (tile_i == g.tiles_per_clip - 1) ? g.N : (t0 + nfr) * g.hop - L / 2;
         float* dxb = dx + (long long)b * g.N;
+        const float* priv0 = smem_f + lay.grp + 2 * L;
+        const int gstep = g.SF * g.hop;
         float part = 0.f;
         for (int i = tid; i < span_used; i += NT) {
             const int p = p0 + i;
             if (p >= 0 && p < g.N) {
-                const float val = dxs[i];
+                float val = 0.f;
+#pragma unroll
+                for (int gi = 0; gi < NG; ++gi) {
+                    const int o = i - gi * gstep;
+                    if (o >= 0 && o < g.sub_span) val += priv0[gi * lay.grp_stride + o];
+                }
                 part += val;
                 if (p >= excl_lo && p < excl_hi) dxb[p] = val;
                 else atomicAdd(dxb + p, val);
@@ -611,72 +691,121 @@ dmel_dft_kernel(const float* __restrict__ x, const float* __restrict__ y_in, con
 // host side: planning + dispatch
 // ----------------------------------------------------------------------------
 constexpr size_t SMEM_MAX = 227 * 1024;
+constexpr int NUM_SMS = 148;
 
-static bool has_fft_plan(int n_fft) {
-    switch (n_fft) {
-        case 128: case 256: case 512: case 1024: case 2048: case 4096: return true;
-        default: return false;
-    }
+template <int L> static PlanDesc plan_desc_of() {
+    PlanDesc d;
+    d.np = Plan<L>::NP;
+    d.r[0] = Plan<L>::R0; d.r[1] = Plan<L>::R1; d.r[2] = Plan<L>::R2; d.r[3] = Plan<L>::R3;
+    return d;
 }
 
-static int fft_threads(int n_fft) {
+struct FftInfo {
+    bool ok;
+    int gt;        // threads per group
+    int tw_total;  // twiddle table entries
+    int ng[2];     // group counts per CTA that are instantiated (largest first)
+    PlanDesc desc;
+};
+
+static FftInfo fft_info(int n_fft) {
+    FftInfo f{};
     switch (n_fft) {
-        case 128: return 128 / Plan<128>::E;
-        case 256: return 256 / Plan<256>::E;
-        case 512: return 512 / Plan<512>::E;
-        case 1024: return 1024 / Plan<1024>::E;
-        case 2048: return 2048 / Plan<2048>::E;
-        case 4096: return 4096 / Plan<4096>::E;
-        default: return 0;
+#define DMEL_FFT_CASE(LL, NGA, NGB)                                                                   \
+    case LL: f.ok = true; f.gt = LL / Plan<LL>::E; f.tw_total = TwTotal<LL>::value; f.ng[0] = NGA;     \
+             f.ng[1] = NGB; f.desc = plan_desc_of<LL>(); break;
+        DMEL_FFT_CASE(128, 8, 4)
+        DMEL_FFT_CASE(256, 8, 4)
+        DMEL_FFT_CASE(512, 8, 4)
+        DMEL_FFT_CASE(1024, 4, 2)
+        DMEL_FFT_CASE(2048, 2, 1)
+        DMEL_FFT_CASE(4096, 1, 1)
+#undef DMEL_FFT_CASE
+        default: f.ok = false; f.desc.np = 0; break;
     }
+    return f;
 }
+
+static bool has_fft_plan(int n_fft) { return fft_info(n_fft).ok; }
 
 struct LaunchPlan {
     int path;  // 0 FFT, 1 direct DFT
-    int TT, span, tiles_per_clip, threads;
+    int NG, SF, TT, span, sub_span, tiles_per_clip, threads;
+    int csr_ints, csr_floats;
     size_t smem;
 };
 
-// Tile size: the largest even TT in {32,16,8,4,2} whose shared memory leaves room for
-// several CTAs per SM; relax the occupancy target until something fits.
-static int plan_launch(int64_t N, int n_fft, int hop, int rows, bool bwd, bool need_dx, LaunchPlan* lp) {
+static size_t smem_bytes_fft(int L, int NG, int tw_total, int span, int sub_span, int M, int TT, int csr_ints,
+                             int csr_floats, bool priv_dx) {
+    return size_t(make_lay(L, NG, tw_total, span, sub_span, M * (TT + 1), csr_ints, csr_floats, priv_dx).total) * 4;
+}
+
+// Tile shape: NG groups x SF frames.  Pick the (NG, SF) that keeps the most warps resident per SM
+// (shared memory and a 16-warp register ceiling at <= 128 registers/thread), discounted by the
+// partial last wave over the 148 SMs; ties go to the larger tile (less halo, fewer staging passes).
+// DMEL_NG / DMEL_SF in the environment pin the choice (tuning experiments).
+static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int csr_ints, int csr_floats, bool bwd,
+                       bool need_dx, LaunchPlan* lp) {
     const int64_t T64 = N / hop + 1;
     if (T64 > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
     const int T = int(T64);
-    if (!has_fft_plan(n_fft)) {
+    lp->csr_ints = csr_ints;
+    lp->csr_floats = csr_floats;
+    const FftInfo fi = fft_info(n_fft);
+    if (!fi.ok) {
         if (n_fft < 2 || n_fft > DMEL_MAX_DFT_NFFT || (n_fft & 1)) return DMEL_ERR_UNSUPPORTED_NFFT;
         const int F = n_fft / 2 + 1;
         lp->path = 1;
-        lp->TT = 1;
-        lp->span = n_fft;
+        lp->NG = 1; lp->SF = 1; lp->TT = 1;
+        lp->span = n_fft; lp->sub_span = n_fft;
         lp->tiles_per_clip = T;
         lp->threads = DFT_THREADS;
         lp->smem = size_t(round_up4(n_fft)) * 4 + size_t(F) * 8 + size_t(round_up4(F) + 8) * 4 + 512;
         if (lp->smem > SMEM_MAX) return DMEL_ERR_SMEM_EXCEEDED;
         return DMEL_OK;
     }
-    const size_t targets[4] = {SMEM_MAX / 4, SMEM_MAX / 3, SMEM_MAX / 2, SMEM_MAX};
-    const int tts[5] = {32, 16, 8, 4, 2};
-    const int t_even = (T + 1) & ~1;
-    for (int ti = 0; ti < 4; ++ti) {
-        for (int c = 0; c < 5; ++c) {
-            int TT = tts[c];
-            if (TT > t_even) TT = t_even;
-            const int64_t span64 = int64_t(TT - 1) * hop + n_fft;
+    int pin_ng = 0, pin_sf = 0;
+    if (const char* e = getenv("DMEL_NG")) pin_ng = atoi(e);
+    if (const char* e = getenv("DMEL_SF")) pin_sf = atoi(e);
+    const int sfs[5] = {16, 8, 4, 2, 32};
+    double best = -1.0;
+    for (int ni = 0; ni < 2; ++ni) {
+        const int NG = fi.ng[ni];
+        if (ni == 1 && NG == fi.ng[0]) break;
+        if (pin_ng && NG != pin_ng) continue;
+        for (int si = 0; si < 5; ++si) {
+            const int SF = sfs[si];
+            if (pin_sf && SF != pin_sf) continue;
+            const int TT = NG * SF;
+            if (!pin_sf && TT > 2 * T + 2 && SF > 2) continue;  // pointless: most groups would idle
+            const int64_t span64 = int64_t(TT - 1) * hop + n_fft, sub64 = int64_t(SF - 1) * hop + n_fft;
             if (span64 > (1 << 20)) continue;
-            const size_t s = smem_bytes_fft(n_fft, int(span64), rows, TT, bwd && need_dx);
-            if (s <= targets[ti]) {
+            const size_t sm = smem_bytes_fft(n_fft, NG, fi.tw_total, int(span64), int(sub64), rows, TT, csr_ints,
+                                             csr_floats, bwd && need_dx);
+            if (sm > SMEM_MAX) continue;
+            const int warps_cta = NG * fi.gt / 32;
+            int ctas = int(SMEM_MAX / (sm + 1024));
+            ctas = std::min(ctas, std::max(1, 16 / warps_cta));
+            ctas = std::min(ctas, 32);
+            if (ctas < 1) ctas = 1;
+            const int tiles = (T + TT - 1) / TT;
+            const double total = double(B) * tiles, slots = double(NUM_SMS) * ctas;
+            const double waves = std::ceil(total / slots);
+            // useful frame slots / offered frame slots (tail tiles are partly empty) x wave fill
+            const double fill = (double(T) / (double(tiles) * TT)) * (total / (waves * slots));
+            const double score = double(ctas * warps_cta) * fill + 1e-3 * TT;
+            if (score > best) {
+                best = score;
                 lp->path = 0;
-                lp->TT = TT;
-                lp->span = int(span64);
-                lp->tiles_per_clip = (T + TT - 1) / TT;
-                lp->threads = fft_threads(n_fft);
-                lp->smem = s;
-                return DMEL_OK;
+                lp->NG = NG; lp->SF = SF; lp->TT = TT;
+                lp->span = int(span64); lp->sub_span = int(sub64);
+                lp->tiles_per_clip = tiles;
+                lp->threads = NG * fi.gt;
+                lp->smem = sm;
             }
         }
     }
-    return DMEL_ERR_SMEM_EXCEEDED;
+    return best < 0 ? DMEL_ERR_SMEM_EXCEEDED : DMEL_OK;
 }
 
 // ---- optional instrumentation for bench.py: launch counter + per-kernel CUDA-event timing.
@@ -734,54 +863,61 @@ static int set_smem(K kernel, size_t smem) {
     return DMEL_OK;
 }
 
-template <int L>
-static int launch_fwd(const float* x, float* y, const Geom& g, const MelDev& mel, bool spec, const WsView& ws,
-                      const LaunchPlan& lp, cudaStream_t st) {
+template <int L, int NG, bool SPEC>
+static int launch_fwd_t(const float* x, float* y, const Geom& g, const MelDev& mel, const WsView& ws,
+                        const LaunchPlan& lp, cudaStream_t st) {
     const unsigned grid = unsigned(int64_t(g.B) * g.tiles_per_clip);
     int rc;
+    if ((rc = set_smem(dmel_fwd_kernel<L, NG, SPEC>, lp.smem))) return rc;
     ProfScope prof(PROF_FWD, st);
-    if (spec) {
-        if ((rc = set_smem(dmel_fwd_kernel<L, true>, lp.smem))) return rc;
-        dmel_fwd_kernel<L, true><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means);
-    } else {
-        if ((rc = set_smem(dmel_fwd_kernel<L, false>, lp.smem))) return rc;
-        dmel_fwd_kernel<L, false><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means);
-    }
+    dmel_fwd_kernel<L, NG, SPEC><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means);
     return check_launch("dmel_fwd_kernel");
 }
 
-template <int L, bool SPEC, bool NEED_DX>
+template <int L, int NG, bool SPEC, bool NEED_DX>
 static int launch_bwd_t(const float* x, const float* y, const float* gy, float* dx, const Geom& g, const MelDev& mel,
                         const WsView& ws, const LaunchPlan& lp, cudaStream_t st) {
     const unsigned grid = unsigned(int64_t(g.B) * g.tiles_per_clip);
     int rc;
-    if ((rc = set_smem(dmel_bwd_kernel<L, SPEC, NEED_DX>, lp.smem))) return rc;
+    if ((rc = set_smem(dmel_bwd_kernel<L, NG, SPEC, NEED_DX>, lp.smem))) return rc;
     ProfScope prof(PROF_BWD, st);
-    dmel_bwd_kernel<L, SPEC, NEED_DX>
+    dmel_bwd_kernel<L, NG, SPEC, NEED_DX>
         <<<grid, lp.threads, lp.smem, st>>>(x, y, gy, dx, g, mel, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
     return check_launch("dmel_bwd_kernel");
 }
 
-template <int L>
+template <int L, int NG>
+static int launch_fwd(const float* x, float* y, const Geom& g, const MelDev& mel, bool spec, const WsView& ws,
+                      const LaunchPlan& lp, cudaStream_t st) {
+    return spec ? launch_fwd_t<L, NG, true>(x, y, g, mel, ws, lp, st) : launch_fwd_t<L, NG, false>(x, y, g, mel, ws, lp, st);
+}
+
+template <int L, int NG>
 static int launch_bwd(const float* x, const float* y, const float* gy, float* dx, const Geom& g, const MelDev& mel,
                       bool spec, const WsView& ws, const LaunchPlan& lp, cudaStream_t st) {
     if (spec) {
-        return dx ? launch_bwd_t<L, true, true>(x, y, gy, dx, g, mel, ws, lp, st)
-                  : launch_bwd_t<L, true, false>(x, y, gy, dx, g, mel, ws, lp, st);
+        return dx ? launch_bwd_t<L, NG, true, true>(x, y, gy, dx, g, mel, ws, lp, st)
+                  : launch_bwd_t<L, NG, true, false>(x, y, gy, dx, g, mel, ws, lp, st);
     }
-    return dx ? launch_bwd_t<L, false, true>(x, y, gy, dx, g, mel, ws, lp, st)
-              : launch_bwd_t<L, false, false>(x, y, gy, dx, g, mel, ws, lp, st);
+    return dx ? launch_bwd_t<L, NG, false, true>(x, y, gy, dx, g, mel, ws, lp, st)
+              : launch_bwd_t<L, NG, false, false>(x, y, gy, dx, g, mel, ws, lp, st);
 }
 
-#define DMEL_DISPATCH_L(n_fft, CALL)              \
-    switch (n_fft) {                              \
-        case 128: rc = CALL(128); break;          \
-        case 256: rc = CALL(256); break;          \
-        case 512: rc = CALL(512); break;          \
-        case 1024: rc = CALL(1024); break;        \
-        case 2048: rc = CALL(2048); break;        \
-        case 4096: rc = CALL(4096); break;        \
-        default: rc = DMEL_ERR_UNSUPPORTED_NFFT;  \
+// (n_fft, NG) -> instantiation; the NG values must match fft_info()
+#define DMEL_DISPATCH(n_fft, ng, CALL)                                   \
+    switch ((n_fft) * 16 + (ng)) {                                       \
+        case 128 * 16 + 8: rc = CALL(128, 8); break;                     \
+        case 128 * 16 + 4: rc = CALL(128, 4); break;                     \
+        case 256 * 16 + 8: rc = CALL(256, 8); break;                     \
+        case 256 * 16 + 4: rc = CALL(256, 4); break;                     \
+        case 512 * 16 + 8: rc = CALL(512, 8); break;                     \
+        case 512 * 16 + 4: rc = CALL(512, 4); break;                     \
+        case 1024 * 16 + 4: rc = CALL(1024, 4); break;                   \
+        case 1024 * 16 + 2: rc = CALL(1024, 2); break;                   \
+        case 2048 * 16 + 2: rc = CALL(2048, 2); break;                   \
+        case 2048 * 16 + 1: rc = CALL(2048, 1); break;                   \
+        case 4096 * 16 + 1: rc = CALL(4096, 1); break;                   \
+        default: rc = DMEL_ERR_UNSUPPORTED_NFFT;                         \
     }
 
 static int validate(const float* x, int64_t B, int64_t N, int64_t stride, int32_t win, int32_t n_fft, int32_t hop,
@@ -792,6 +928,8 @@ static int validate(const float* x, int64_t B, int64_t N, int64_t stride, int32_
     if (n_mels > 0) {
         if (!bank) return DMEL_ERR_NULL_POINTER;
         if (bank->n_mels != n_mels || bank->n_freqs != n_fft / 2 + 1) return DMEL_ERR_BAD_MELBANK;
+        if (bank->mel_nnz < 0 || bank->bin_nnz < 0 || bank->mel_nnz > (1 << 22) || bank->bin_nnz > (1 << 22))
+            return DMEL_ERR_BAD_MELBANK;
         if (!bank->mel_k0 || !bank->mel_off || !bank->mel_w || !bank->bin_m0 || !bank->bin_off || !bank->bin_w)
             return DMEL_ERR_NULL_POINTER;
     }
@@ -812,7 +950,7 @@ static int run_prep(const float* x, int64_t B, int64_t N, int64_t stride, float 
                     int32_t flags, const WsView& ws, cudaStream_t st) {
     ProfScope prof(PROF_PREP, st);
     dmel_prep_kernel<<<unsigned(B + 1), PREP_THREADS, 0, st>>>(x, stride, int(B), int(N), lam_abs, win, n_fft,
-                                                                flags, ws);
+                                                                flags, ws, fft_info(n_fft).desc);
     return check_launch("dmel_prep_kernel");
 }
 
@@ -862,13 +1000,18 @@ extern "C" DMEL_API size_t dmel_workspace_bytes(int64_t batch, int32_t n_fft) {
     return ws_bytes(batch, n_fft);
 }
 
-extern "C" DMEL_API int dmel_query_launch(int64_t n_points, int32_t n_fft, int32_t hop, int32_t rows, int32_t which,
-                                 int32_t* tile_frames, int32_t* smem_bytes, int32_t* threads, int32_t* path) {
-    if (n_points <= 0 || hop <= 0 || n_fft <= 0 || rows <= 0) return DMEL_ERR_BAD_GEOMETRY;
+extern "C" DMEL_API int dmel_query_launch(int64_t batch, int64_t n_points, int32_t n_fft, int32_t hop, int32_t rows,
+                                          int32_t bank_nnz, int32_t which, int32_t* tile_frames,
+                                          int32_t* groups, int32_t* smem_bytes, int32_t* threads, int32_t* path) {
+    if (batch <= 0 || n_points <= 0 || hop <= 0 || n_fft <= 0 || rows <= 0 || bank_nnz < 0) return DMEL_ERR_BAD_GEOMETRY;
     LaunchPlan lp{};
-    int rc = plan_launch(n_points, n_fft, hop, rows, which != 0, which == 1, &lp);
+    const int F = n_fft / 2 + 1;
+    const bool spec = bank_nnz == 0;
+    const int ci = spec ? 0 : (which == 0 ? 2 * rows + 1 : 2 * F + 1);
+    int rc = plan_launch(batch, n_points, n_fft, hop, rows, ci, bank_nnz, which != 0, which == 1, &lp);
     if (rc) return rc;
     if (tile_frames) *tile_frames = lp.TT;
+    if (groups) *groups = lp.NG;
     if (smem_bytes) *smem_bytes = int32_t(lp.smem);
     if (threads) *threads = lp.threads;
     if (path) *path = lp.path;
@@ -885,8 +1028,12 @@ static Geom make_geom(int64_t B, int64_t N, int64_t stride, int32_t n_fft, int32
     g.n_fft = n_fft;
     g.M = rows;
     g.TT = lp.TT;
+    g.SF = lp.SF;
     g.tiles_per_clip = lp.tiles_per_clip;
     g.span = lp.span;
+    g.sub_span = lp.sub_span;
+    g.csr_ints = lp.csr_ints;
+    g.csr_floats = lp.csr_floats;
     g.x_stride = stride;
     g.log_eps = log_eps;
     return g;
@@ -903,7 +1050,9 @@ extern "C" DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t 
     const bool spec = (n_mels == 0);
     const int rows = spec ? n_fft / 2 + 1 : n_mels;
     LaunchPlan lp{};
-    if ((rc = plan_launch(n_points, n_fft, hop, rows, false, false, &lp))) return rc;
+    if ((rc = plan_launch(batch, n_points, n_fft, hop, rows, spec ? 0 : 2 * n_mels + 1, spec ? 0 : bank->mel_nnz, false,
+                          false, &lp)))
+        return rc;
     if (int64_t(batch) * lp.tiles_per_clip > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
     WsView ws = ws_view(workspace, batch, n_fft);
     if ((rc = run_prep(x, batch, n_points, x_row_stride, fabsf(lambda), win_length, n_fft, flags, ws, st)))
@@ -917,8 +1066,8 @@ extern "C" DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t 
             x, nullptr, nullptr, y, nullptr, g, mel, spec ? 1 : 0, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
         return check_launch("dmel_dft_kernel<fwd>");
     }
-#define CALL_FWD(LL) launch_fwd<LL>(x, y, g, mel, spec, ws, lp, st)
-    DMEL_DISPATCH_L(n_fft, CALL_FWD)
+#define CALL_FWD(LL, NGG) launch_fwd<LL, NGG>(x, y, g, mel, spec, ws, lp, st)
+    DMEL_DISPATCH(n_fft, lp.NG, CALL_FWD)
 #undef CALL_FWD
     return rc;
 }
@@ -937,7 +1086,9 @@ extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t
     const int rows = spec ? n_fft / 2 + 1 : n_mels;
     const bool need_dx = grad_x != nullptr;
     LaunchPlan lp{};
-    if ((rc = plan_launch(n_points, n_fft, hop, rows, true, need_dx, &lp))) return rc;
+    if ((rc = plan_launch(batch, n_points, n_fft, hop, rows, spec ? 0 : 2 * (n_fft / 2 + 1) + 1,
+                          spec ? 0 : bank->bin_nnz, true, need_dx, &lp)))
+        return rc;
     if (int64_t(batch) * lp.tiles_per_clip > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
     WsView ws = ws_view(workspace, batch, n_fft);
     if (!prepared) {
@@ -968,8 +1119,8 @@ extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t
         }
         if ((rc = check_launch("dmel_dft_kernel<bwd>"))) return rc;
     } else {
-#define CALL_BWD(LL) launch_bwd<LL>(x, y, grad_y, grad_x, g, mel, spec, ws, lp, st)
-        DMEL_DISPATCH_L(n_fft, CALL_BWD)
+#define CALL_BWD(LL, NGG) launch_bwd<LL, NGG>(x, y, grad_y, grad_x, g, mel, spec, ws, lp, st)
+        DMEL_DISPATCH(n_fft, lp.NG, CALL_BWD)
 #undef CALL_BWD
         if (rc) return rc;
     }

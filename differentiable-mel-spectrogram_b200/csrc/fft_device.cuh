@@ -1,8 +1,9 @@
 // fft_device.cuh — in-register / shared-memory complex FFT building blocks (sm_100a).
 //
-// One CTA computes one L-point complex FFT at a time ("packed pair": two real STFT
-// frames ride as the real and imaginary part of one complex transform).  Each of
-// the NT = L/E threads keeps E complex points in registers; a Stockham pass is
+// A group of GT = L/E threads (one warp for L <= 512) computes one L-point complex FFT at
+// a time ("packed pair": two real STFT frames ride as the real and imaginary part of one
+// complex transform); a CTA runs several such groups independently.  Each thread keeps
+// E complex points in registers; a Stockham pass is
 //   load (stride L/R)  ->  twiddle  ->  radix-R DFT in registers  ->  scatter (stride NS)
 // with the scatter/gather going through a ping-pong pair of shared-memory buffers.
 // The shared-memory index is XOR-swizzled per pass so that both the strided scatter
@@ -97,22 +98,37 @@ template <> struct RegDft<16> {
 };
 
 // ----------------------------------------------------------------------------
-// FFT plans: E points per thread, NP passes, radices R[p]  (prod R = L)
+// FFT plans.  A *group* of GT = L/E threads owns one L-point transform; a CTA hosts
+// several independent groups.  L <= 512 use a single warp per transform (E up to 16
+// points per thread), so their exchanges need only __syncwarp; larger L use 2..8 warps
+// and a named barrier private to the group.  prod R = L.
 // ----------------------------------------------------------------------------
 template <int L> struct Plan;
 template <> struct Plan<128>  { static constexpr int E = 4,  NP = 4, R0 = 4,  R1 = 4,  R2 = 4,  R3 = 2; };
 template <> struct Plan<256>  { static constexpr int E = 8,  NP = 3, R0 = 8,  R1 = 8,  R2 = 4,  R3 = 1; };
-template <> struct Plan<512>  { static constexpr int E = 8,  NP = 3, R0 = 8,  R1 = 8,  R2 = 8,  R3 = 1; };
+template <> struct Plan<512>  { static constexpr int E = 16, NP = 3, R0 = 8,  R1 = 8,  R2 = 8,  R3 = 1; };
 template <> struct Plan<1024> { static constexpr int E = 16, NP = 3, R0 = 16, R1 = 8,  R2 = 8,  R3 = 1; };
 template <> struct Plan<2048> { static constexpr int E = 16, NP = 3, R0 = 16, R1 = 16, R2 = 8,  R3 = 1; };
 template <> struct Plan<4096> { static constexpr int E = 16, NP = 3, R0 = 16, R1 = 16, R2 = 16, R3 = 1; };
-template <> struct Plan<8192> { static constexpr int E = 16, NP = 4, R0 = 16, R1 = 8,  R2 = 8,  R3 = 8; };
 
 template <int L, int P> struct PlanRadix;
 template <int L> struct PlanRadix<L, 0> { static constexpr int R = Plan<L>::R0, NS = 1; };
 template <int L> struct PlanRadix<L, 1> { static constexpr int R = Plan<L>::R1, NS = Plan<L>::R0; };
 template <int L> struct PlanRadix<L, 2> { static constexpr int R = Plan<L>::R2, NS = Plan<L>::R0 * Plan<L>::R1; };
 template <int L> struct PlanRadix<L, 3> { static constexpr int R = Plan<L>::R3, NS = Plan<L>::R0 * Plan<L>::R1 * Plan<L>::R2; };
+
+// Per-pass twiddle tables, concatenated: pass p >= 1 owns (R_p - 1) rows of NS_p entries,
+//   T_p[r-1][k] = exp(-2*pi*i * k*r / (NS_p*R_p)),  k < NS_p
+// so a warp reads consecutive k (conflict-free) at an immediate row offset.
+template <int L, int P> struct TwOffset {
+    static constexpr int value = TwOffset<L, P - 1>::value + (PlanRadix<L, P - 1>::R - 1) * PlanRadix<L, P - 1>::NS;
+};
+template <int L> struct TwOffset<L, 1> { static constexpr int value = 0; };
+template <int L> struct TwOffset<L, 0> { static constexpr int value = 0; };
+template <int L> struct TwTotal {
+    static constexpr int value = TwOffset<L, Plan<L>::NP - 1>::value +
+                                 (PlanRadix<L, Plan<L>::NP - 1>::R - 1) * PlanRadix<L, Plan<L>::NP - 1>::NS;
+};
 
 // XOR swizzle of a float2 index inside a 16-entry (128 B) row. `ROT` is chosen per
 // pass (see swz_rot) so that the scatter with stride NS lands on 16 distinct 8-byte
@@ -125,14 +141,23 @@ __host__ __device__ constexpr int swz_rot(int NS, int R) {
     return NS >= 16 ? 0 : ((NS * R >= 16) ? (16 / R) : NS);
 }
 
+// barrier over the GT threads of one group (bar_id in 1..15 is private to the group)
+template <int GT> __device__ __forceinline__ void group_sync(int bar_id) {
+    if (GT == 32) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(GT) : "memory");
+    }
+}
+
 // ----------------------------------------------------------------------------
 // One Stockham pass, split in its three phases so callers can place barriers.
-//   v[i*R + r]  holds input  j + r*(L/R),  j = tid + i*NT   (after gather)
+//   v[i*R + r]  holds input  j + r*(L/R),  j = gtid + i*GT   (after gather)
 //   after compute it holds output index  (j-k)*R + k + r*NS, k = j mod NS
 // ----------------------------------------------------------------------------
 template <int L, int P> struct Pass {
     static constexpr int E = Plan<L>::E;
-    static constexpr int NT = L / E;
+    static constexpr int GT = L / E;
     static constexpr int R = PlanRadix<L, P>::R;
     static constexpr int NS = PlanRadix<L, P>::NS;
     static constexpr int NB = E / R;       // butterflies per thread
@@ -141,29 +166,29 @@ template <int L, int P> struct Pass {
     // the layout this pass reads is the one the previous pass wrote
     static constexpr int ROT_IN = (P == 0) ? 0 : swz_rot(PlanRadix<L, (P > 0 ? P - 1 : 0)>::NS,
                                                           PlanRadix<L, (P > 0 ? P - 1 : 0)>::R);
+    static constexpr int TW_OFF = TwOffset<L, P>::value;
 
-    static __device__ __forceinline__ void gather(float2 (&v)[E], const float2* __restrict__ in, int tid) {
+    static __device__ __forceinline__ void gather(float2 (&v)[E], const float2* __restrict__ in, int gtid) {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            const int j = tid + i * NT;
+            const int j = gtid + i * GT;
 #pragma unroll
             for (int r = 0; r < R; ++r) v[i * R + r] = in[swz<ROT_IN>(j + r * STR)];
         }
     }
 
-    // twiddle (table tw[i] = exp(-2*pi*i*idx/L), idx in [0,L)) + radix-R DFT in registers
-    static __device__ __forceinline__ void compute(float2 (&v)[E], const float2* __restrict__ tw, int tid) {
+    // twiddle (shared-memory tables, see TwOffset) + radix-R DFT in registers
+    static __device__ __forceinline__ void compute(float2 (&v)[E], const float2* __restrict__ twt, int gtid) {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            const int j = tid + i * NT;
+            const int j = gtid + i * GT;
             float2 t[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) t[r] = v[i * R + r];
             if (NS > 1) {
-                const int k = j & (NS - 1);
-                const int base = k * (L / (NS * R));
+                const float2* row = twt + TW_OFF + (j & (NS - 1));
 #pragma unroll
-                for (int r = 1; r < R; ++r) t[r] = cmul(t[r], __ldg(&tw[base * r]));
+                for (int r = 1; r < R; ++r) t[r] = cmul(t[r], row[(r - 1) * NS]);
             }
             RegDft<R>::run(t);
 #pragma unroll
@@ -171,10 +196,10 @@ template <int L, int P> struct Pass {
         }
     }
 
-    static __device__ __forceinline__ void scatter(const float2 (&v)[E], float2* __restrict__ out, int tid) {
+    static __device__ __forceinline__ void scatter(const float2 (&v)[E], float2* __restrict__ out, int gtid) {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            const int j = tid + i * NT;
+            const int j = gtid + i * GT;
             const int k = j & (NS - 1);
             const int j0 = (j - k) * R + k;
 #pragma unroll
@@ -183,35 +208,34 @@ template <int L, int P> struct Pass {
     }
 
     // output index held in v[i*R + r] after compute()
-    static __device__ __forceinline__ int out_index(int tid, int i, int r) {
-        const int j = tid + i * NT;
+    static __device__ __forceinline__ int out_index(int gtid, int i, int r) {
+        const int j = gtid + i * GT;
         const int k = j & (NS - 1);
         return (j - k) * R + k + r * NS;
     }
 };
 
-// Runs passes FIRST..NP-1 of the plan.  On entry v holds the gathered inputs of pass
-// FIRST.  Intermediate results ping-pong through buf[sel], buf[sel^1] ...; `sel` is
-// advanced on every scatter so that callers can keep toggling across iterations.
-// If STORE_LAST the natural-order spectrum ends in buf[last written] (linear layout,
-// the last pass always has NS >= 16) and a barrier has been passed; otherwise the last
-// pass leaves its outputs in v (index map Pass<L,NP-1>::out_index) and does not sync.
+// Runs passes P..NP-1 of the plan for one group, exchanging through ONE shared-memory buffer.
+// On entry v holds the gathered inputs of pass P.  A group barrier precedes every scatter (all
+// earlier readers of `buf` — the previous pass's gathers, or the previous iteration's consumers —
+// are done) and follows it.  If STORE_LAST the natural-order spectrum ends in `buf` (linear
+// layout: the last pass always has NS >= 16) behind a barrier; otherwise the last pass leaves
+// its outputs in v (index map Pass<L,NP-1>::out_index).
 template <int L, int P, bool STORE_LAST>
-__device__ __forceinline__ void run_passes(float2 (&v)[Plan<L>::E], float2* buf0, float2* buf1, int& sel,
-                                           const float2* __restrict__ tw, int tid) {
-    Pass<L, P>::compute(v, tw, tid);
+__device__ __forceinline__ void run_passes(float2 (&v)[Plan<L>::E], float2* buf, const float2* __restrict__ twt,
+                                           int gtid, int bar_id) {
+    constexpr int GT = L / Plan<L>::E;
+    Pass<L, P>::compute(v, twt, gtid);
     if constexpr (P + 1 < Plan<L>::NP) {
-        float2* out = sel ? buf1 : buf0;
-        Pass<L, P>::scatter(v, out, tid);
-        sel ^= 1;
-        __syncthreads();
-        Pass<L, P + 1>::gather(v, out, tid);
-        run_passes<L, P + 1, STORE_LAST>(v, buf0, buf1, sel, tw, tid);
+        group_sync<GT>(bar_id);
+        Pass<L, P>::scatter(v, buf, gtid);
+        group_sync<GT>(bar_id);
+        Pass<L, P + 1>::gather(v, buf, gtid);
+        run_passes<L, P + 1, STORE_LAST>(v, buf, twt, gtid, bar_id);
     } else if constexpr (STORE_LAST) {
-        float2* out = sel ? buf1 : buf0;
-        Pass<L, P>::scatter(v, out, tid);
-        sel ^= 1;
-        __syncthreads();
+        group_sync<GT>(bar_id);
+        Pass<L, P>::scatter(v, buf, gtid);
+        group_sync<GT>(bar_id);
     }
 }
 

@@ -115,6 +115,7 @@ class DeviceBank:
         ip, fp = self._ints.data_ptr(), self._flts.data_ptr()
         s = MelBankStruct()
         s.n_freqs, s.n_mels = F, M
+        s.mel_nnz, s.bin_nnz = int(packed.mel_off[-1]), int(packed.bin_off[-1])
         s.mel_k0 = ip
         s.mel_off = ip + 4 * M
         s.bin_m0 = ip + 4 * (M + M + 1)

@@ -178,11 +178,13 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
     return DmelFunction.apply(x, lambd, geo, bank, eps, flags, lam_value)
 
 
-def query_launch(n_points: int, n_fft: int, hop: int, rows: int, which: int = 0) -> Tuple[int, int, int, int]:
-    """(tile_frames, smem_bytes, threads, path) the launcher would use; path 0 = FFT, 1 = DFT."""
+def query_launch(batch: int, n_points: int, n_fft: int, hop: int, rows: int, bank_nnz: int = 0,
+                 which: int = 0) -> dict:
+    """What the launcher would pick: frames per CTA tile, FFT groups per CTA, dynamic shared memory, threads per
+    CTA and the path (0 = FFT, 1 = direct DFT).  which: 0 fwd, 1 bwd (dx + dlambda), 2 bwd (dlambda only)."""
     import ctypes
     lib = _lib.load()
-    a, b, c, d = (ctypes.c_int32() for _ in range(4))
-    _lib.check(lib.dmel_query_launch(n_points, n_fft, hop, rows, which, ctypes.byref(a), ctypes.byref(b),
-                                     ctypes.byref(c), ctypes.byref(d)), "dmel_query_launch")
-    return a.value, b.value, c.value, d.value
+    v = [ctypes.c_int32() for _ in range(5)]
+    _lib.check(lib.dmel_query_launch(batch, n_points, n_fft, hop, rows, bank_nnz, which, *[ctypes.byref(a) for a in v]),
+               "dmel_query_launch")
+    return dict(tile_frames=v[0].value, groups=v[1].value, smem_bytes=v[2].value, threads=v[3].value, path=v[4].value)

@@ -62,6 +62,8 @@ typedef enum dmel_status {
 typedef struct dmel_melbank {
     int32_t n_freqs;          /* F = n_fft/2 + 1                                        */
     int32_t n_mels;           /* M                                                      */
+    int32_t mel_nnz;          /* = mel_off[M]  (entries of mel_w)                       */
+    int32_t bin_nnz;          /* = bin_off[F]  (entries of bin_w)                       */
     const int32_t* mel_k0;    /* [M]                                                    */
     const int32_t* mel_off;   /* [M+1]                                                  */
     const float* mel_w;       /* [mel_off[M]]                                           */
@@ -124,11 +126,13 @@ DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t n_points, 
                       void* workspace, size_t workspace_bytes, int32_t prepared,
                       void* cuda_stream);
 
-/* Introspection for tests / benchmarks: tile size (frames per CTA), dynamic shared
- * memory and threads per CTA the launcher would pick.  which: 0 fwd, 1 bwd (dx+dlambda),
- * 2 bwd (dlambda only).  Returns DMEL_OK or an error.                               */
-DMEL_API int dmel_query_launch(int64_t n_points, int32_t n_fft, int32_t hop, int32_t rows, int32_t which,
-                      int32_t* tile_frames, int32_t* smem_bytes, int32_t* threads, int32_t* path);
+/* Introspection for tests / benchmarks: tile size (frames per CTA), FFT groups per CTA,
+ * dynamic shared memory and threads per CTA the launcher would pick.  rows = n_mels or
+ * n_fft/2+1; bank_nnz = entries of the sparse bank form that pass stages (0 in spectrogram
+ * mode); which: 0 fwd, 1 bwd (dx+dlambda), 2 bwd (dlambda only).                      */
+DMEL_API int dmel_query_launch(int64_t batch, int64_t n_points, int32_t n_fft, int32_t hop, int32_t rows,
+                      int32_t bank_nnz, int32_t which, int32_t* tile_frames, int32_t* groups,
+                      int32_t* smem_bytes, int32_t* threads, int32_t* path);
 
 /* Instrumentation (bench.py): cumulative number of kernels this library launched, by kind
  * (0 prep, 1 forward, 2 backward, 3 finalize, <0 all); and opt-in per-launch CUDA-event timing of

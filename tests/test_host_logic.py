@@ -93,12 +93,16 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_device():
 
 
 def test_launch_plans_fit_shared_memory():
-    for (N, L, hop, rows) in [(8000, 512, 80, 64), (220500, 2048, 441, 128), (160000, 1024, 160, 128), (8000, 4096, 80, 64),
-                              (8000, 128, 80, 64), (256, 512, 1, 257), (128, 256, 1, 129), (8000, 256, 80, 64)]:
+    for (B, N, L, hop, rows) in [(256, 8000, 512, 80, 64), (128, 220500, 2048, 441, 128), (1024, 160000, 1024, 160, 128),
+                                 (512, 8000, 4096, 80, 64), (512, 8000, 128, 80, 64), (64, 256, 512, 1, 0), (128, 128, 256, 1, 0),
+                                 (512, 8000, 256, 80, 64), (1, 50, 512, 80, 8)]:
+        spec = rows == 0
+        r = rows if rows else L // 2 + 1
         for which in (0, 1, 2):
-            tt, smem, threads, path = dm.query_launch(N, L, hop, rows, which)
-            assert path == 0 and smem <= 227 * 1024 and tt % 2 == 0 and threads in (32, 64, 128, 256)
-    assert dm.query_launch(100, 200, 5, 101, 1)[3] == 1           # non power of two -> direct DFT path
+            q = dm.query_launch(B, N, L, hop, r, 0 if spec else 2 * (L // 2 + 1), which)
+            assert q["path"] == 0 and q["smem_bytes"] <= 227 * 1024 and q["tile_frames"] % 2 == 0, q
+            assert q["threads"] in (128, 256) and q["groups"] in (1, 2, 4, 8), q
+    assert dm.query_launch(2, 100, 200, 5, 101, 0, 1)["path"] == 1           # non power of two -> direct DFT path
 
 
 def test_layers_keep_the_reference_contract_and_refuse_cpu():
