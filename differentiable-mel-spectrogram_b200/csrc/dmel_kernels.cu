@@ -93,6 +93,7 @@ struct Geom {
     int csr_ints, csr_floats;    // size of the sparse-bank form the kernel stages (0 in spectrogram mode)
     long long x_stride;
     float log_eps;
+    int row_aligned;             // x and x_stride are 16-byte aligned: spans may move as 16-byte quads
 };
 
 struct MelDev {
@@ -243,7 +244,7 @@ __host__ __device__ inline SmemLay make_lay(int L, int NG, int tw_total, int spa
     int o = 0;
     l.twt = o;   o += round_up4(2 * tw_total);
     l.win = o;   o += L;
-    l.xs = o;    o += round_up4(span);
+    l.xs = o;    o += round_up4(span + 4);   // + up to 3 words of 16-byte phase shift
     l.tile = o;  o += round_up4(tile_words);
     l.csr_i = o; o += round_up4(csr_ints);
     l.csr_w = o; o += round_up4(csr_floats);
@@ -256,7 +257,80 @@ __host__ __device__ inline SmemLay make_lay(int L, int NG, int tw_total, int spa
 }
 
 // ----------------------------------------------------------------------------
-// forward
+// asynchronous staging helpers (LDGSTS: global -> shared without a register round trip)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+// 4-byte copy; valid == false writes a zero instead (src-size 0 => zero fill, nothing is read)
+__device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    const int n = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// copy `words` 4-byte words (multiple of 4; both pointers 16-byte aligned) with the whole CTA
+template <int NT>
+__device__ __forceinline__ void stage_table_async(float* dst, const void* src, int words, int tid) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = tid; i < (words >> 2); i += NT) cp_async16(d4 + i, s4 + i);
+}
+
+// Stage the signal span [p0, p0+span) of one clip: out-of-range samples are zero (center=True,
+// pad_mode='constant').  Issue phase only; call span_centre() after cp_async_wait_all().
+// The span is stored at xs + shift (shift = p0 mod 4 in [0,3]) so that shared and global
+// addresses share their 16-byte phase and whole in-range quads move as one 16-byte copy.
+template <int NT>
+__device__ __forceinline__ void span_issue(float* xs_sh, const float* __restrict__ xb, int p0, int span, int N,
+                                           bool row_aligned, int tid) {
+    // quad q covers span indices [4q - shift, 4q - shift + 3]  <->  xs_sh storage words [4q, 4q+3] (before +shift)
+    const int shift = p0 & 3;                       // p0 may be negative: & 3 is still the mod-4 phase
+    float* base = xs_sh;                            // storage word i + shift holds span index i
+    const int nq = (span + shift + 3) >> 2;
+    for (int q = tid; q < nq; q += NT) {
+        const int i0 = 4 * q - shift;               // span index of the quad's first word
+        const int p = p0 + i0;                      // global sample index, multiple of 4 by construction
+        float* d = base + 4 * q;
+        if (row_aligned && i0 >= 0 && i0 + 3 < span && p >= 0 && p + 3 < N) {
+            cp_async16(d, xb + p);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int pe = p + e, ie = i0 + e;
+                const bool ok = (ie >= 0) && (ie < span) && (pe >= 0) && (pe < N);
+                cp_async4_zfill(d + e, xb + (ok ? pe : 0), ok);
+            }
+        }
+    }
+}
+
+// remove the clip mean from the in-range samples this thread staged (same q loop as span_issue,
+// so every thread only touches words whose copies it has itself waited for)
+template <int NT>
+__device__ __forceinline__ void span_centre(float* xs_sh, int p0, int span, int N, float mu, int tid) {
+    const int shift = p0 & 3;
+    const int nq = (span + shift + 3) >> 2;
+    for (int q = tid; q < nq; q += NT) {
+        const int i0 = 4 * q - shift;
+        const int p = p0 + i0;
+        float4* d = reinterpret_cast<float4*>(xs_sh + 4 * q);
+        float4 v = *d;
+        v.x = (p + 0 >= 0 && p + 0 < N) ? v.x - mu : 0.f;
+        v.y = (p + 1 >= 0 && p + 1 < N) ? v.y - mu : 0.f;
+        v.z = (p + 2 >= 0 && p + 2 < N) ? v.z - mu : 0.f;
+        v.w = (p + 3 >= 0 && p + 3 < N) ? v.w - mu : 0.f;
+        *d = v;
+    }
+}
+
+// integer log2 of a power of two
+__device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
+
+// ----------------------------------------------------------------------------
+// forward (persistent: each CTA stages the constant tables once and walks tiles)
 // ----------------------------------------------------------------------------
 template <int L, int NG, bool SPEC>
 __global__ void __launch_bounds__(NG * (L / Plan<L>::E))
@@ -269,7 +343,7 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
     const SmemLay lay = make_lay(L, NG, TWN, g.span, g.sub_span, g.M * TS, g.csr_ints, g.csr_floats, false);
     float2* twt = reinterpret_cast<float2*>(smem_f + lay.twt);
     float* win = smem_f + lay.win;
-    float* xs = smem_f + lay.xs;
+    float* xs_sh = smem_f + lay.xs;
     float* tile = smem_f + lay.tile;
     int* csr_i = reinterpret_cast<int*>(smem_f + lay.csr_i);
     float* csr_w = smem_f + lay.csr_w;
@@ -277,93 +351,115 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
     const int tid = threadIdx.x;
     const int grp = tid / GT, gtid = tid - grp * GT, bar_id = 1 + grp;
     float2* buf = reinterpret_cast<float2*>(smem_f + lay.grp + grp * lay.grp_stride);
-    const int b = blockIdx.x / g.tiles_per_clip;
-    const int tile_i = blockIdx.x - b * g.tiles_per_clip;
-    const int t0 = tile_i * g.TT;
-    const int nfr = min(g.TT, g.T - t0);
-
-    // stage everything the tile needs, once
-    for (int i = tid; i < TWN; i += NT) twt[i] = __ldg(tw_g + i);
-    for (int i = tid; i < L; i += NT) win[i] = __ldg(win_g + i);
-    if (!SPEC) {
-        // mel-major sparse bank: ints = k0[M] | off[M+1], floats = weights
-        for (int i = tid; i < g.M; i += NT) csr_i[i] = __ldg(mel.mel_k0 + i);
-        for (int i = tid; i <= g.M; i += NT) csr_i[g.M + i] = __ldg(mel.mel_off + i);
-        for (int i = tid; i < g.csr_floats; i += NT) csr_w[i] = __ldg(mel.mel_w + i);
-    }
-    {
-        const float mu = __ldg(means + b);
-        const float* xb = x + (long long)b * g.x_stride;
-        const int p0 = t0 * g.hop - L / 2;
-        for (int i = tid; i < g.span; i += NT) {
-            const int p = p0 + i;
-            xs[i] = (p >= 0 && p < g.N) ? __ldg(xb + p) - mu : 0.f;
-        }
-    }
-    __syncthreads();
-
-    const int f_hi = min(grp * g.SF + g.SF, nfr);
-    for (int f = grp * g.SF; f < f_hi; f += 2) {
-        const float* xa = xs + f * g.hop;
-        const float* xb2 = xa + g.hop;
-        float2 v[E];
-#pragma unroll
-        for (int i = 0; i < P0::NB; ++i) {
-            const int j = gtid + i * GT;
-#pragma unroll
-            for (int r = 0; r < P0::R; ++r) {
-                const int n = j + r * P0::STR;
-                const float w = win[n];
-                v[i * P0::R + r] = make_float2(xa[n] * w, xb2[n] * w);
-            }
-        }
-        run_passes<L, 0, true>(v, buf, twt, gtid, bar_id);
-        // packed pair -> two one-sided power spectra (time_frequency.py:53), in place
-        for (int k = gtid; k <= L / 2; k += GT) {
-            const float2 z1 = buf[k];
-            const float2 z2 = buf[(L - k) & (L - 1)];
-            const float ar = 0.5f * (z1.x + z2.x), ai = 0.5f * (z1.y - z2.y);
-            const float br = 0.5f * (z1.y + z2.y), bi = 0.5f * (z2.x - z1.x);
-            const float pa = fmaf(ar, ar, ai * ai), pb = fmaf(br, br, bi * bi);
-            if (SPEC) {
-                tile[k * TS + f] = pa;
-                tile[k * TS + f + 1] = pb;
-            } else {
-                buf[k] = make_float2(pa, pb);
-            }
-        }
-        if (!SPEC) {
-            group_sync<GT>(bar_id);
-            // models.py:53 matmul(spec^T, mel_fb): each mel reads its contiguous run of bins
-            for (int m = gtid; m < g.M; m += GT) {
-                const int k0 = csr_i[m];
-                const int o0 = csr_i[g.M + m], o1 = csr_i[g.M + m + 1];
-                float sa = 0.f, sb = 0.f;
-                for (int o = o0; o < o1; ++o) {
-                    const float w = csr_w[o];
-                    const float2 p = buf[k0 + (o - o0)];
-                    sa = fmaf(w, p.x, sa);
-                    sb = fmaf(w, p.y, sb);
-                }
-                tile[m * TS + f] = sa;
-                tile[m * TS + f + 1] = sb;
-            }
-        }
-    }
-    __syncthreads();
-    // models.py:54 pack into (B,1,M,T), T fastest; optional fused log (models.py:72-73)
-    float* yb = y + (long long)b * g.M * g.T + t0;
+    const bool row_aligned = g.row_aligned != 0;
+    const int tt_shift = ilog2(g.TT);
     const bool do_log = g.log_eps >= 0.f;
-    for (int idx = tid; idx < g.M * nfr; idx += NT) {
-        const int m = idx / nfr, tt = idx - m * nfr;
-        float val = tile[m * TS + tt];
-        if (do_log) val = logf(val + g.log_eps);
-        yb[(long long)m * g.T + tt] = val;
+
+    // constant tables: once per CTA
+    stage_table_async<NT>(smem_f + lay.twt, tw_g, 2 * TWN, tid);
+    stage_table_async<NT>(win, win_g, L, tid);
+    if (!SPEC) {
+        // mel-major sparse bank: ints = k0[M4] | off[..], floats = weights (sub-arrays padded to 4 words)
+        stage_table_async<NT>(reinterpret_cast<float*>(csr_i), mel.mel_k0, round_up4(g.M), tid);
+        stage_table_async<NT>(reinterpret_cast<float*>(csr_i + round_up4(g.M)), mel.mel_off, round_up4(g.M + 1), tid);
+        stage_table_async<NT>(csr_w, mel.mel_w, round_up4(g.csr_floats), tid);
     }
+    const int* s_k0 = csr_i;
+    const int* s_off = csr_i + round_up4(g.M);
+
+    const int total_tiles = g.B * g.tiles_per_clip;
+    for (int tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
+        const int b = tix / g.tiles_per_clip;
+        const int tile_i = tix - b * g.tiles_per_clip;
+        const int t0 = tile_i * g.TT;
+        const int nfr = min(g.TT, g.T - t0);
+        const int p0 = t0 * g.hop - L / 2;
+        const float* xb = x + (long long)b * g.x_stride;
+        const float* xs = xs_sh + (p0 & 3);
+
+        span_issue<NT>(xs_sh, xb, p0, g.span, g.N, row_aligned, tid);
+        const float mu = __ldg(means + b);
+        cp_async_wait_all();
+        span_centre<NT>(xs_sh, p0, g.span, g.N, mu, tid);
+        __syncthreads();
+
+        const int f_hi = min(grp * g.SF + g.SF, nfr);
+        for (int f = grp * g.SF; f < f_hi; f += 2) {
+            const float* xa = xs + f * g.hop;
+            const float* xb2 = xa + g.hop;
+            float2 v[E];
+#pragma unroll
+            for (int i = 0; i < P0::NB; ++i) {
+                const int j = gtid + i * GT;
+#pragma unroll
+                for (int r = 0; r < P0::R; ++r) {
+                    const int n = j + r * P0::STR;
+                    const float w = win[n];
+                    v[i * P0::R + r] = make_float2(xa[n] * w, xb2[n] * w);
+                }
+            }
+            run_passes<L, 0, true>(v, buf, twt, gtid, bar_id);
+            // packed pair -> two one-sided power spectra (time_frequency.py:53), in place
+#pragma unroll 4
+            for (int k = gtid; k <= L / 2; k += GT) {
+                const float2 z1 = buf[k];
+                const float2 z2 = buf[(L - k) & (L - 1)];
+                const float ar = 0.5f * (z1.x + z2.x), ai = 0.5f * (z1.y - z2.y);
+                const float br = 0.5f * (z1.y + z2.y), bi = 0.5f * (z2.x - z1.x);
+                const float pa = fmaf(ar, ar, ai * ai), pb = fmaf(br, br, bi * bi);
+                if (SPEC) {
+                    tile[k * TS + f] = pa;
+                    tile[k * TS + f + 1] = pb;
+                } else {
+                    buf[k] = make_float2(pa, pb);
+                }
+            }
+            if (!SPEC) {
+                group_sync<GT>(bar_id);
+                // models.py:53 matmul(spec^T, mel_fb): each mel reads its contiguous run of bins.
+                // 4 taps in flight per step; taps past the run get weight 0 (the bins read are valid memory)
+                for (int m = gtid; m < g.M; m += GT) {
+                    const int k0 = s_k0[m];
+                    const int o0 = s_off[m], o1 = s_off[m + 1];
+                    const float2* pp = buf + k0;
+                    float sa = 0.f, sb = 0.f;
+                    for (int o = o0; o < o1; o += 4) {
+                        float w[4];
+                        float2 p[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            w[u] = (o + u < o1) ? csr_w[o + u] : 0.f;
+                            p[u] = pp[min(o + u - o0, L / 2)];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            sa = fmaf(w[u], p[u].x, sa);
+                            sb = fmaf(w[u], p[u].y, sb);
+                        }
+                    }
+                    tile[m * TS + f] = sa;
+                    tile[m * TS + f + 1] = sb;
+                }
+            }
+        }
+        __syncthreads();
+        // models.py:54 pack into (B,1,M,T), T fastest; optional fused log (models.py:72-73)
+        float* yb = y + (long long)b * g.M * g.T + t0;
+        for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
+            const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
+            if (tt < nfr) {
+                float val = tile[m * TS + tt];
+                if (do_log) val = logf(val + g.log_eps);
+                yb[(long long)m * g.T + tt] = val;
+            }
+        }
+        // the next iteration's staging only writes xs; its __syncthreads orders it after this epilogue
+    }
+    cp_async_wait_all();
 }
 
 // ----------------------------------------------------------------------------
-// backward
+// backward (persistent)
 // ----------------------------------------------------------------------------
 template <int L, int NG, bool SPEC, bool NEED_DX>
 __global__ void __launch_bounds__(NG * (L / Plan<L>::E))
@@ -380,7 +476,7 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
     const SmemLay lay = make_lay(L, NG, TWN, g.span, g.sub_span, g.M * TS, g.csr_ints, g.csr_floats, NEED_DX);
     float2* twt = reinterpret_cast<float2*>(smem_f + lay.twt);
     float* win = smem_f + lay.win;
-    float* xs = smem_f + lay.xs;
+    float* xs_sh = smem_f + lay.xs;
     float* gt = smem_f + lay.tile;
     int* csr_i = reinterpret_cast<int*>(smem_f + lay.csr_i);
     float* csr_w = smem_f + lay.csr_w;
@@ -390,164 +486,182 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
     const int grp = tid / GT, gtid = tid - grp * GT, bar_id = 1 + grp;
     float2* buf = reinterpret_cast<float2*>(smem_f + lay.grp + grp * lay.grp_stride);
     float* priv = smem_f + lay.grp + grp * lay.grp_stride + 2 * L;   // this group's dx sub-span
-    const int b = blockIdx.x / g.tiles_per_clip;
-    const int tile_i = blockIdx.x - b * g.tiles_per_clip;
-    const int t0 = tile_i * g.TT;
-    const int nfr = min(g.TT, g.T - t0);
-    const int p0 = t0 * g.hop - L / 2;
+    const bool row_aligned = g.row_aligned != 0;
+    const int tt_shift = ilog2(g.TT);
+    const bool do_log = g.log_eps >= 0.f;
 
-    for (int i = tid; i < TWN; i += NT) twt[i] = __ldg(tw_g + i);
-    for (int i = tid; i < L; i += NT) win[i] = __ldg(win_g + i);
+    stage_table_async<NT>(smem_f + lay.twt, tw_g, 2 * TWN, tid);
+    stage_table_async<NT>(win, win_g, L, tid);
     if (!SPEC) {
-        // bin-major sparse bank: ints = m0[F] | off[F+1], floats = weights
-        for (int i = tid; i < F; i += NT) csr_i[i] = __ldg(mel.bin_m0 + i);
-        for (int i = tid; i <= F; i += NT) csr_i[F + i] = __ldg(mel.bin_off + i);
-        for (int i = tid; i < g.csr_floats; i += NT) csr_w[i] = __ldg(mel.bin_w + i);
+        // bin-major sparse bank: ints = m0[F4] | off[..], floats = weights
+        stage_table_async<NT>(reinterpret_cast<float*>(csr_i), mel.bin_m0, round_up4(F), tid);
+        stage_table_async<NT>(reinterpret_cast<float*>(csr_i + round_up4(F)), mel.bin_off, round_up4(F + 1), tid);
+        stage_table_async<NT>(csr_w, mel.bin_w, round_up4(g.csr_floats), tid);
     }
-    {
-        const float mu = __ldg(means + b);
-        const float* xb = x + (long long)b * g.x_stride;
-        for (int i = tid; i < g.span; i += NT) {
-            const int p = p0 + i;
-            xs[i] = (p >= 0 && p < g.N) ? __ldg(xb + p) - mu : 0.f;
-        }
-    }
-    if (NEED_DX)
-        for (int i = gtid; i < g.sub_span; i += GT) priv[i] = 0.f;
-    {
-        // upstream gradient tile; with the fused log dL/dmel = G / (mel + eps) = G * exp(-y)
-        const bool do_log = g.log_eps >= 0.f;
-        const long long base = (long long)b * g.M * g.T + t0;
-        for (int idx = tid; idx < g.M * g.TT; idx += NT) {
-            const int m = idx / g.TT, tt = idx - m * g.TT;
-            float val = 0.f;
-            if (tt < nfr) {
-                const long long off = base + (long long)m * g.T + tt;
-                val = __ldg(gy + off);
-                if (do_log) val *= expf(-__ldg(y + off));
-            }
-            gt[m * TS + tt] = val;
-        }
-    }
-    __syncthreads();
-
+    const int* s_m0 = csr_i;
+    const int* s_off = csr_i + round_up4(F);
     const float inv_lam3 = hdr->inv_lam3, cprime = hdr->cprime, centre = hdr->centre;
     float dlam = 0.f;
-    const int f_lo = grp * g.SF;
-    const int f_hi = min(f_lo + g.SF, nfr);
-    for (int f = f_lo; f < f_hi; f += 2) {
-        const float* xa = xs + f * g.hop;
-        const float* xb2 = xa + g.hop;
-        const bool has_b = (f + 1) < nfr;
-        float2 v[E];
-#pragma unroll
-        for (int i = 0; i < P0::NB; ++i) {
-            const int j = gtid + i * GT;
-#pragma unroll
-            for (int r = 0; r < P0::R; ++r) {
-                const int n = j + r * P0::STR;
-                const float w = win[n];
-                v[i * P0::R + r] = make_float2(xa[n] * w, xb2[n] * w);
+
+    const int total_tiles = g.B * g.tiles_per_clip;
+    for (int tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
+        const int b = tix / g.tiles_per_clip;
+        const int tile_i = tix - b * g.tiles_per_clip;
+        const int t0 = tile_i * g.TT;
+        const int nfr = min(g.TT, g.T - t0);
+        const int p0 = t0 * g.hop - L / 2;
+        const float* xb = x + (long long)b * g.x_stride;
+        const float* xs = xs_sh + (p0 & 3);
+
+        span_issue<NT>(xs_sh, xb, p0, g.span, g.N, row_aligned, tid);
+        const float mu = __ldg(means + b);
+        if (NEED_DX)
+            for (int i = gtid; i < g.sub_span; i += GT) priv[i] = 0.f;
+        {
+            // upstream gradient tile; with the fused log dL/dmel = G / (mel + eps) = G * exp(-y)
+            const long long base = (long long)b * g.M * g.T + t0;
+            for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
+                const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
+                float val = 0.f;
+                if (tt < nfr) {
+                    const long long off = base + (long long)m * g.T + tt;
+                    val = __ldg(gy + off);
+                    if (do_log) val *= __expf(-__ldg(y + off));
+                }
+                gt[m * TS + tt] = val;
             }
         }
-        run_passes<L, 0, true>(v, buf, twt, gtid, bar_id);
-        // buf <- conj(V),  V = Zhat_a + i*Zhat_b the Hermitian-extended 2*GP*X of both frames
-        for (int k = gtid; k <= L / 2; k += GT) {
-            const float2 z1 = buf[k];
-            const float2 z2 = buf[(L - k) & (L - 1)];
-            const float ar = 0.5f * (z1.x + z2.x), ai = 0.5f * (z1.y - z2.y);
-            const float br = 0.5f * (z1.y + z2.y), bi = 0.5f * (z2.x - z1.x);
-            float ga = 0.f, gb = 0.f;
-            if (SPEC) {
-                ga = gt[k * TS + f];
-                gb = gt[k * TS + f + 1];
-            } else {
-                const int m0 = csr_i[k];
-                const int o0 = csr_i[F + k], o1 = csr_i[F + k + 1];
-                for (int o = o0; o < o1; ++o) {
-                    const float w = csr_w[o];
-                    const float* gp = gt + (m0 + (o - o0)) * TS + f;
-                    ga = fmaf(w, gp[0], ga);
-                    gb = fmaf(w, gp[1], gb);
+        cp_async_wait_all();
+        span_centre<NT>(xs_sh, p0, g.span, g.N, mu, tid);
+        __syncthreads();
+
+        const int f_lo = grp * g.SF;
+        const int f_hi = min(f_lo + g.SF, nfr);
+        for (int f = f_lo; f < f_hi; f += 2) {
+            const float* xa = xs + f * g.hop;
+            const float* xb2 = xa + g.hop;
+            const bool has_b = (f + 1) < nfr;
+            float2 v[E];
+#pragma unroll
+            for (int i = 0; i < P0::NB; ++i) {
+                const int j = gtid + i * GT;
+#pragma unroll
+                for (int r = 0; r < P0::R; ++r) {
+                    const int n = j + r * P0::STR;
+                    const float w = win[n];
+                    v[i * P0::R + r] = make_float2(xa[n] * w, xb2[n] * w);
                 }
             }
-            if (k == 0 || k == L / 2) {
-                buf[k] = make_float2(2.f * ga * ar, -2.f * gb * br);
-            } else {
-                buf[k] = make_float2(ga * ar - gb * bi, -(ga * ai + gb * br));
-                buf[L - k] = make_float2(ga * ar + gb * bi, ga * ai - gb * br);
+            run_passes<L, 0, true>(v, buf, twt, gtid, bar_id);
+            // buf <- conj(V),  V = Zhat_a + i*Zhat_b the Hermitian-extended 2*GP*X of both frames
+#pragma unroll 2
+            for (int k = gtid; k <= L / 2; k += GT) {
+                const float2 z1 = buf[k];
+                const float2 z2 = buf[(L - k) & (L - 1)];
+                const float ar = 0.5f * (z1.x + z2.x), ai = 0.5f * (z1.y - z2.y);
+                const float br = 0.5f * (z1.y + z2.y), bi = 0.5f * (z2.x - z1.x);
+                float ga, gb;
+                if (SPEC) {
+                    ga = gt[k * TS + f];
+                    gb = gt[k * TS + f + 1];
+                } else {
+                    // <= 2 taps per bin for a triangular bank: both issued together; longer runs loop
+                    const int m0 = s_m0[k];
+                    const int o0 = s_off[k], o1 = s_off[k + 1];
+                    const float w0 = (o0 < o1) ? csr_w[o0] : 0.f;
+                    const float w1 = (o0 + 1 < o1) ? csr_w[o0 + 1] : 0.f;
+                    const float* gp0 = gt + m0 * TS + f;
+                    const float* gp1 = gt + min(m0 + 1, g.M - 1) * TS + f;
+                    ga = fmaf(w1, gp1[0], w0 * gp0[0]);
+                    gb = fmaf(w1, gp1[1], w0 * gp0[1]);
+                    for (int o = o0 + 2; o < o1; ++o) {
+                        const float w = csr_w[o];
+                        const float* gp = gt + (m0 + (o - o0)) * TS + f;
+                        ga = fmaf(w, gp[0], ga);
+                        gb = fmaf(w, gp[1], gb);
+                    }
+                }
+                if (k == 0 || k == L / 2) {
+                    buf[k] = make_float2(2.f * ga * ar, -2.f * gb * br);
+                } else {
+                    buf[k] = make_float2(ga * ar - gb * bi, -(ga * ai + gb * br));
+                    buf[L - k] = make_float2(ga * ar + gb * bi, ga * ai - gb * br);
+                }
             }
-        }
-        group_sync<GT>(bar_id);
-        // inverse transform as conj(FFT(conj(V))): u_a = Re, u_b = -Im of the FFT output
-        P0::gather(v, buf, gtid);
-        run_passes<L, 0, false>(v, buf, twt, gtid, bar_id);
-        // dL/dlambda, time-domain form: sum_n u[n] * fr[n] * dw/dlambda[n],
-        //   dw/dlambda[n] = w[n] * ((n-centre)^2/lambda^3 - cprime)
-#pragma unroll
-        for (int i = 0; i < PL::NB; ++i) {
-#pragma unroll
-            for (int r = 0; r < PL::R; ++r) {
-                const int n = PL::out_index(gtid, i, r);
-                const float2 u = v[i * PL::R + r];
-                const float w = win[n];
-                const float d = float(n) - centre;
-                const float q = fmaf(d * d, inv_lam3, -cprime);
-                const float sdot = u.x * xa[n] - (has_b ? u.y * xb2[n] : 0.f);
-                dlam = fmaf(w * q, sdot, dlam);
-                v[i * PL::R + r] = make_float2(u.x * w, -u.y * w);
-            }
-        }
-        if (NEED_DX) {
-            // overlap-add (adjoint of the framing) into the group's private span:
-            // frame a, barrier, frame b, barrier — no shared-memory atomics
-            float* da = priv + (f - f_lo) * g.hop;
-#pragma unroll
-            for (int i = 0; i < PL::NB; ++i)
-#pragma unroll
-                for (int r = 0; r < PL::R; ++r) da[PL::out_index(gtid, i, r)] += v[i * PL::R + r].x;
             group_sync<GT>(bar_id);
-            if (has_b) {
-                float* db = da + g.hop;
+            // inverse transform as conj(FFT(conj(V))): u_a = Re, u_b = -Im of the FFT output
+            P0::gather(v, buf, gtid);
+            run_passes<L, 0, false>(v, buf, twt, gtid, bar_id);
+            // dL/dlambda, time-domain form: sum_n u[n] * fr[n] * dw/dlambda[n],
+            //   dw/dlambda[n] = w[n] * ((n-centre)^2/lambda^3 - cprime)
+#pragma unroll
+            for (int i = 0; i < PL::NB; ++i) {
+#pragma unroll
+                for (int r = 0; r < PL::R; ++r) {
+                    const int n = PL::out_index(gtid, i, r);
+                    const float2 u = v[i * PL::R + r];
+                    const float w = win[n];
+                    const float d = float(n) - centre;
+                    const float q = fmaf(d * d, inv_lam3, -cprime);
+                    const float sdot = u.x * xa[n] - (has_b ? u.y * xb2[n] : 0.f);
+                    dlam = fmaf(w * q, sdot, dlam);
+                    v[i * PL::R + r] = make_float2(u.x * w, -u.y * w);
+                }
+            }
+            if (NEED_DX) {
+                // overlap-add (adjoint of the framing) into the group's private span:
+                // frame a, barrier, frame b, barrier — no shared-memory atomics
+                float* da = priv + (f - f_lo) * g.hop;
 #pragma unroll
                 for (int i = 0; i < PL::NB; ++i)
 #pragma unroll
-                    for (int r = 0; r < PL::R; ++r) db[PL::out_index(gtid, i, r)] += v[i * PL::R + r].y;
-            }
-            group_sync<GT>(bar_id);
-        }
-    }
-
-    const double tot = block_sum(double(dlam), red);   // contains __syncthreads: private spans are complete
-    if (tid == 0) atomicAdd(&hdr->dlam_acc, tot);
-
-    if (NEED_DX) {
-        // merge the groups' sub-spans; crop the centre padding; positions no other tile touches are
-        // stored, the halos shared with the neighbouring tiles are reduced into the zeroed dx
-        const int span_used = (nfr - 1) * g.hop + L;
-        const int excl_lo = (tile_i == 0) ? 0 : (t0 - 1) * g.hop + L / 2;
-        const int excl_hi = (tile_i == g.tiles_per_clip - 1) ? g.N : (t0 + nfr) * g.hop - L / 2;
-        float* dxb = dx + (long long)b * g.N;
-        const float* priv0 = smem_f + lay.grp + 2 * L;
-        const int gstep = g.SF * g.hop;
-        float part = 0.f;
-        for (int i = tid; i < span_used; i += NT) {
-            const int p = p0 + i;
-            if (p >= 0 && p < g.N) {
-                float val = 0.f;
+                    for (int r = 0; r < PL::R; ++r) da[PL::out_index(gtid, i, r)] += v[i * PL::R + r].x;
+                group_sync<GT>(bar_id);
+                if (has_b) {
+                    float* db = da + g.hop;
 #pragma unroll
-                for (int gi = 0; gi < NG; ++gi) {
-                    const int o = i - gi * gstep;
-                    if (o >= 0 && o < g.sub_span) val += priv0[gi * lay.grp_stride + o];
+                    for (int i = 0; i < PL::NB; ++i)
+#pragma unroll
+                        for (int r = 0; r < PL::R; ++r) db[PL::out_index(gtid, i, r)] += v[i * PL::R + r].y;
                 }
-                part += val;
-                if (p >= excl_lo && p < excl_hi) dxb[p] = val;
-                else atomicAdd(dxb + p, val);
+                group_sync<GT>(bar_id);
             }
         }
-        const double cs = block_sum(double(part), red);
-        if (tid == 0) atomicAdd(clipsum + b, cs);
+
+        if (NEED_DX) {
+            __syncthreads();   // all private spans of this tile are complete
+            // merge the groups' sub-spans; crop the centre padding; positions no other tile touches are
+            // stored, the halos shared with the neighbouring tiles are reduced into the zeroed dx
+            const int span_used = (nfr - 1) * g.hop + L;
+            const int excl_lo = (tile_i == 0) ? 0 : (t0 - 1) * g.hop + L / 2;
+            const int excl_hi = (tile_i == g.tiles_per_clip - 1) ? g.N : (t0 + nfr) * g.hop - L / 2;
+            float* dxb = dx + (long long)b * g.N;
+            const float* priv0 = smem_f + lay.grp + 2 * L;
+            const int gstep = g.SF * g.hop;
+            float part = 0.f;
+            for (int i = tid; i < span_used; i += NT) {
+                const int p = p0 + i;
+                if (p >= 0 && p < g.N) {
+                    float val = 0.f;
+#pragma unroll
+                    for (int gi = 0; gi < NG; ++gi) {
+                        const int o = i - gi * gstep;
+                        if (o >= 0 && o < g.sub_span) val += priv0[gi * lay.grp_stride + o];
+                    }
+                    part += val;
+                    if (p >= excl_lo && p < excl_hi) dxb[p] = val;
+                    else atomicAdd(dxb + p, val);
+                }
+            }
+            // per-clip sum of dx for the mean-removal adjoint (one fp64 atomic per warp)
+            double ps = warp_sum(double(part));
+            if ((tid & 31) == 0) atomicAdd(clipsum + b, ps);
+        }
+        __syncthreads();   // next tile restages xs / gt / priv
     }
+    cp_async_wait_all();
+    const double tot = block_sum(double(dlam), red);
+    if (tid == 0) atomicAdd(&hdr->dlam_acc, tot);
 }
 
 // ----------------------------------------------------------------------------
@@ -863,12 +977,29 @@ static int set_smem(K kernel, size_t smem) {
     return DMEL_OK;
 }
 
+// persistent launch: one resident wave of CTAs (occupancy x SM count), each walking tiles with stride gridDim
+template <typename K>
+static unsigned persistent_grid(K kernel, const LaunchPlan& lp, int64_t total_tiles) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, lp.threads, lp.smem) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        per_sm = 1;
+    }
+    int sms = NUM_SMS, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+    }
+    const int64_t cap = int64_t(per_sm) * sms;
+    return unsigned(std::min<int64_t>(total_tiles, cap));
+}
+
 template <int L, int NG, bool SPEC>
 static int launch_fwd_t(const float* x, float* y, const Geom& g, const MelDev& mel, const WsView& ws,
                         const LaunchPlan& lp, cudaStream_t st) {
-    const unsigned grid = unsigned(int64_t(g.B) * g.tiles_per_clip);
     int rc;
     if ((rc = set_smem(dmel_fwd_kernel<L, NG, SPEC>, lp.smem))) return rc;
+    const unsigned grid = persistent_grid(dmel_fwd_kernel<L, NG, SPEC>, lp, int64_t(g.B) * g.tiles_per_clip);
     ProfScope prof(PROF_FWD, st);
     dmel_fwd_kernel<L, NG, SPEC><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means);
     return check_launch("dmel_fwd_kernel");
@@ -877,9 +1008,9 @@ static int launch_fwd_t(const float* x, float* y, const Geom& g, const MelDev& m
 template <int L, int NG, bool SPEC, bool NEED_DX>
 static int launch_bwd_t(const float* x, const float* y, const float* gy, float* dx, const Geom& g, const MelDev& mel,
                         const WsView& ws, const LaunchPlan& lp, cudaStream_t st) {
-    const unsigned grid = unsigned(int64_t(g.B) * g.tiles_per_clip);
     int rc;
     if ((rc = set_smem(dmel_bwd_kernel<L, NG, SPEC, NEED_DX>, lp.smem))) return rc;
+    const unsigned grid = persistent_grid(dmel_bwd_kernel<L, NG, SPEC, NEED_DX>, lp, int64_t(g.B) * g.tiles_per_clip);
     ProfScope prof(PROF_BWD, st);
     dmel_bwd_kernel<L, NG, SPEC, NEED_DX>
         <<<grid, lp.threads, lp.smem, st>>>(x, y, gy, dx, g, mel, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
@@ -932,6 +1063,10 @@ static int validate(const float* x, int64_t B, int64_t N, int64_t stride, int32_
             return DMEL_ERR_BAD_MELBANK;
         if (!bank->mel_k0 || !bank->mel_off || !bank->mel_w || !bank->bin_m0 || !bank->bin_off || !bank->bin_w)
             return DMEL_ERR_NULL_POINTER;
+        const uintptr_t al = reinterpret_cast<uintptr_t>(bank->mel_k0) | reinterpret_cast<uintptr_t>(bank->mel_off) |
+                             reinterpret_cast<uintptr_t>(bank->mel_w) | reinterpret_cast<uintptr_t>(bank->bin_m0) |
+                             reinterpret_cast<uintptr_t>(bank->bin_off) | reinterpret_cast<uintptr_t>(bank->bin_w);
+        if (al & 15) return DMEL_ERR_BAD_MELBANK;  // the arrays are staged with 16-byte async copies
     }
     if (ws_bytes_in < ws_bytes(B, n_fft)) return DMEL_ERR_WORKSPACE_TOO_SMALL;
     return DMEL_OK;
@@ -1007,7 +1142,7 @@ extern "C" DMEL_API int dmel_query_launch(int64_t batch, int64_t n_points, int32
     LaunchPlan lp{};
     const int F = n_fft / 2 + 1;
     const bool spec = bank_nnz == 0;
-    const int ci = spec ? 0 : (which == 0 ? 2 * rows + 1 : 2 * F + 1);
+    const int ci = spec ? 0 : (which == 0 ? round_up4(rows) + round_up4(rows + 1) : round_up4(F) + round_up4(F + 1));
     int rc = plan_launch(batch, n_points, n_fft, hop, rows, ci, bank_nnz, which != 0, which == 1, &lp);
     if (rc) return rc;
     if (tile_frames) *tile_frames = lp.TT;
@@ -1036,6 +1171,7 @@ static Geom make_geom(int64_t B, int64_t N, int64_t stride, int32_t n_fft, int32
     g.csr_floats = lp.csr_floats;
     g.x_stride = stride;
     g.log_eps = log_eps;
+    g.row_aligned = 0;
     return g;
 }
 
@@ -1050,14 +1186,15 @@ extern "C" DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t 
     const bool spec = (n_mels == 0);
     const int rows = spec ? n_fft / 2 + 1 : n_mels;
     LaunchPlan lp{};
-    if ((rc = plan_launch(batch, n_points, n_fft, hop, rows, spec ? 0 : 2 * n_mels + 1, spec ? 0 : bank->mel_nnz, false,
+    if ((rc = plan_launch(batch, n_points, n_fft, hop, rows, spec ? 0 : round_up4(n_mels) + round_up4(n_mels + 1), spec ? 0 : bank->mel_nnz, false,
                           false, &lp)))
         return rc;
     if (int64_t(batch) * lp.tiles_per_clip > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
     WsView ws = ws_view(workspace, batch, n_fft);
     if ((rc = run_prep(x, batch, n_points, x_row_stride, fabsf(lambda), win_length, n_fft, flags, ws, st)))
         return rc;
-    const Geom g = make_geom(batch, n_points, x_row_stride, n_fft, hop, rows, log_eps, lp);
+    Geom g = make_geom(batch, n_points, x_row_stride, n_fft, hop, rows, log_eps, lp);
+    g.row_aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_row_stride & 3) == 0) ? 1 : 0;
     const MelDev mel = mel_dev(bank);
     if (lp.path == 1) {
         if ((rc = set_smem(dmel_dft_kernel<false, false>, lp.smem))) return rc;
@@ -1086,7 +1223,7 @@ extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t
     const int rows = spec ? n_fft / 2 + 1 : n_mels;
     const bool need_dx = grad_x != nullptr;
     LaunchPlan lp{};
-    if ((rc = plan_launch(batch, n_points, n_fft, hop, rows, spec ? 0 : 2 * (n_fft / 2 + 1) + 1,
+    if ((rc = plan_launch(batch, n_points, n_fft, hop, rows, spec ? 0 : round_up4(n_fft / 2 + 1) + round_up4(n_fft / 2 + 2),
                           spec ? 0 : bank->bin_nnz, true, need_dx, &lp)))
         return rc;
     if (int64_t(batch) * lp.tiles_per_clip > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
@@ -1103,7 +1240,8 @@ extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t
         if (cudaMemsetAsync(grad_x, 0, size_t(batch) * size_t(n_points) * sizeof(float), st) != cudaSuccess)
             return check_launch("memset grad_x");
     }
-    const Geom g = make_geom(batch, n_points, x_row_stride, n_fft, hop, rows, log_eps, lp);
+    Geom g = make_geom(batch, n_points, x_row_stride, n_fft, hop, rows, log_eps, lp);
+    g.row_aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_row_stride & 3) == 0) ? 1 : 0;
     const MelDev mel = mel_dev(bank);
     if (lp.path == 1) {
         const unsigned grid = unsigned(int64_t(g.B) * g.T);

@@ -107,21 +107,25 @@ class DeviceBank:
     def __init__(self, packed: PackedBank, device: torch.device):
         self.packed = packed
         self.device = device
-        ints = np.concatenate([packed.mel_k0, packed.mel_off, packed.bin_m0, packed.bin_off]).astype(np.int32)
-        flts = np.concatenate([packed.mel_w, packed.bin_w]).astype(np.float32)
-        self._ints = torch.from_numpy(ints).to(device)
-        self._flts = torch.from_numpy(flts).to(device)
-        M, F = packed.n_mels, packed.n_freqs
-        ip, fp = self._ints.data_ptr(), self._flts.data_ptr()
+        # one blob, every sub-array on a 16-byte boundary and padded to a multiple of 4 elements
+        # (the kernels stage them with 16-byte cp.async copies)
+        parts = [packed.mel_k0.astype(np.int32), packed.mel_off.astype(np.int32), packed.bin_m0.astype(np.int32),
+                 packed.bin_off.astype(np.int32), packed.mel_w.astype(np.float32).view(np.int32),
+                 packed.bin_w.astype(np.float32).view(np.int32)]
+        offs, words = [], 0
+        for a in parts:
+            offs.append(words)
+            words += (a.size + 3) // 4 * 4 + 4
+        blob = np.zeros(words, np.int32)
+        for o, a in zip(offs, parts):
+            blob[o:o + a.size] = a
+        self._blob = torch.from_numpy(blob).to(device)
+        base = self._blob.data_ptr()
+        assert base % 16 == 0
         s = MelBankStruct()
-        s.n_freqs, s.n_mels = F, M
+        s.n_freqs, s.n_mels = packed.n_freqs, packed.n_mels
         s.mel_nnz, s.bin_nnz = int(packed.mel_off[-1]), int(packed.bin_off[-1])
-        s.mel_k0 = ip
-        s.mel_off = ip + 4 * M
-        s.bin_m0 = ip + 4 * (M + M + 1)
-        s.bin_off = ip + 4 * (M + M + 1 + F)
-        s.mel_w = fp
-        s.bin_w = fp + 4 * packed.mel_w.size
+        s.mel_k0, s.mel_off, s.bin_m0, s.bin_off, s.mel_w, s.bin_w = (base + 4 * o for o in offs)
         self.struct = s
 
     def ref(self):

@@ -58,7 +58,9 @@ typedef enum dmel_status {
  *       cnt = mel_off[m+1]-mel_off[m], weights mel_w[mel_off[m] + i]
  *   bin-major (backward gather): bin k reads mels  bin_m0[k] .. bin_m0[k]+cnt-1,
  *       cnt = bin_off[k+1]-bin_off[k], weights bin_w[bin_off[k] + i]
- * All six arrays are device pointers; the struct itself lives on the host.       */
+ * All six arrays are device pointers, each 16-byte aligned and readable up to the next
+ * multiple of 4 elements (they are staged into shared memory with 16-byte async copies);
+ * the struct itself lives on the host.                                              */
 typedef struct dmel_melbank {
     int32_t n_freqs;          /* F = n_fft/2 + 1                                        */
     int32_t n_mels;           /* M                                                      */
