@@ -416,26 +416,22 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
             }
             if (!SPEC) {
                 group_sync<GT>(bar_id);
-                // models.py:53 matmul(spec^T, mel_fb): each mel reads its contiguous run of bins.
-                // 4 taps in flight per step; taps past the run get weight 0 (the bins read are valid memory)
+                // models.py:53 matmul(spec^T, mel_fb): each mel reads its contiguous run of bins.  Runs are
+                // zero-padded to a multiple of 4 taps by the host (dmel.h), so 4 taps go per step with one
+                // 16-byte weight load; the bins behind a padded tap are valid shared memory (k0+run <= L/2+3 < L)
                 for (int m = gtid; m < g.M; m += GT) {
                     const int k0 = s_k0[m];
                     const int o0 = s_off[m], o1 = s_off[m + 1];
                     const float2* pp = buf + k0;
+                    const float4* wp = reinterpret_cast<const float4*>(csr_w + o0);
                     float sa = 0.f, sb = 0.f;
-                    for (int o = o0; o < o1; o += 4) {
-                        float w[4];
-                        float2 p[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            w[u] = (o + u < o1) ? csr_w[o + u] : 0.f;
-                            p[u] = pp[min(o + u - o0, L / 2)];
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            sa = fmaf(w[u], p[u].x, sa);
-                            sb = fmaf(w[u], p[u].y, sb);
-                        }
+                    for (int q = 0; q < ((o1 - o0) >> 2); ++q) {
+                        const float4 w = wp[q];
+                        const float2 a0 = pp[4 * q], a1 = pp[4 * q + 1], a2 = pp[4 * q + 2], a3 = pp[4 * q + 3];
+                        sa = fmaf(w.x, a0.x, sa); sb = fmaf(w.x, a0.y, sb);
+                        sa = fmaf(w.y, a1.x, sa); sb = fmaf(w.y, a1.y, sb);
+                        sa = fmaf(w.z, a2.x, sa); sb = fmaf(w.z, a2.y, sb);
+                        sa = fmaf(w.w, a3.x, sa); sb = fmaf(w.w, a3.y, sb);
                     }
                     tile[m * TS + f] = sa;
                     tile[m * TS + f + 1] = sb;
@@ -449,7 +445,8 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
             const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
             if (tt < nfr) {
                 float val = tile[m * TS + tt];
-                if (do_log) val = logf(val + g.log_eps);
+                // lg2.approx * ln2: <= 3 ulp, i.e. ~1e-6 absolute on log-mel values (budget 1e-5 + 1e-4 |y|)
+                if (do_log) val = __logf(val + g.log_eps);
                 yb[(long long)m * g.T + tt] = val;
             }
         }
@@ -473,11 +470,12 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
     using PL = Pass<L, NP - 1>;
     extern __shared__ __align__(16) float smem_f[];
     const int TS = g.TT + 1;
-    const SmemLay lay = make_lay(L, NG, TWN, g.span, g.sub_span, g.M * TS, g.csr_ints, g.csr_floats, NEED_DX);
+    const SmemLay lay = make_lay(L, NG, TWN, g.span, g.sub_span, 2 * round_up4(g.M * TS), g.csr_ints, g.csr_floats, NEED_DX);
     float2* twt = reinterpret_cast<float2*>(smem_f + lay.twt);
     float* win = smem_f + lay.win;
     float* xs_sh = smem_f + lay.xs;
     float* gt = smem_f + lay.tile;
+    float* yt = gt + round_up4(g.M * TS);   // raw y tile (fused log only)
     int* csr_i = reinterpret_cast<int*>(smem_f + lay.csr_i);
     float* csr_w = smem_f + lay.csr_w;
     double* red = reinterpret_cast<double*>(smem_f + lay.red);
@@ -518,21 +516,26 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
         if (NEED_DX)
             for (int i = gtid; i < g.sub_span; i += GT) priv[i] = 0.f;
         {
-            // upstream gradient tile; with the fused log dL/dmel = G / (mel + eps) = G * exp(-y)
+            // upstream gradient tile (and y when the log is fused): rows are T floats apart in HBM, so the
+            // copies are 4-byte async ones, all in flight together; columns past the last frame are zero
             const long long base = (long long)b * g.M * g.T + t0;
             for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
                 const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
-                float val = 0.f;
-                if (tt < nfr) {
-                    const long long off = base + (long long)m * g.T + tt;
-                    val = __ldg(gy + off);
-                    if (do_log) val *= __expf(-__ldg(y + off));
-                }
-                gt[m * TS + tt] = val;
+                const bool ok = tt < nfr;
+                const long long off = base + (long long)m * g.T + (ok ? tt : 0);
+                cp_async4_zfill(gt + m * TS + tt, gy + off, ok);
+                if (do_log) cp_async4_zfill(yt + m * TS + tt, y + off, ok);
             }
         }
         cp_async_wait_all();
         span_centre<NT>(xs_sh, p0, g.span, g.N, mu, tid);
+        if (do_log) {
+            // dL/dmel = G / (mel + eps) = G * exp(-y); each thread touches the words it copied itself
+            for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
+                const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
+                gt[m * TS + tt] *= __expf(-yt[m * TS + tt]);
+            }
+        }
         __syncthreads();
 
         const int f_lo = grp * g.SF;
@@ -850,8 +853,10 @@ struct LaunchPlan {
 };
 
 static size_t smem_bytes_fft(int L, int NG, int tw_total, int span, int sub_span, int M, int TT, int csr_ints,
-                             int csr_floats, bool priv_dx) {
-    return size_t(make_lay(L, NG, tw_total, span, sub_span, M * (TT + 1), csr_ints, csr_floats, priv_dx).total) * 4;
+                             int csr_floats, bool bwd, bool priv_dx) {
+    // backward keeps two tiles (dL/dy and, for the fused log, y)
+    const int tile_words = bwd ? 2 * round_up4(M * (TT + 1)) : M * (TT + 1);
+    return size_t(make_lay(L, NG, tw_total, span, sub_span, tile_words, csr_ints, csr_floats, priv_dx).total) * 4;
 }
 
 // Tile shape: NG groups x SF frames.  Pick the (NG, SF) that keeps the most warps resident per SM
@@ -895,7 +900,7 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
             const int64_t span64 = int64_t(TT - 1) * hop + n_fft, sub64 = int64_t(SF - 1) * hop + n_fft;
             if (span64 > (1 << 20)) continue;
             const size_t sm = smem_bytes_fft(n_fft, NG, fi.tw_total, int(span64), int(sub64), rows, TT, csr_ints,
-                                             csr_floats, bwd && need_dx);
+                                             csr_floats, bwd, bwd && need_dx);
             if (sm > SMEM_MAX) continue;
             const int warps_cta = NG * fi.gt / 32;
             int ctas = int(SMEM_MAX / (sm + 1024));

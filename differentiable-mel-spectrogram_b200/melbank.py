@@ -75,13 +75,17 @@ def pack_bank(fb: np.ndarray) -> PackedBank:
 
     k0, kcnt = runs(nz.T)   # per mel: run of bins
     m0, mcnt = runs(nz)     # per bin: run of mels
+    # the forward kernel consumes 4 taps per step: pad every mel run with zero weights to a multiple of 4
+    # (bins read behind the run stay <= F+2, inside the kernel's L-entry spectrum buffer)
+    kcnt_true = kcnt.copy()
+    kcnt = ((kcnt + 3) // 4 * 4).astype(np.int32)
     mel_off = np.zeros(M + 1, np.int32)
     mel_off[1:] = np.cumsum(kcnt)
     bin_off = np.zeros(F + 1, np.int32)
     bin_off[1:] = np.cumsum(mcnt)
     mel_w = np.zeros(max(int(mel_off[-1]), 1), np.float32)
     for m in range(M):
-        mel_w[mel_off[m]:mel_off[m + 1]] = fb[k0[m]:k0[m] + kcnt[m], m]
+        mel_w[mel_off[m]:mel_off[m] + kcnt_true[m]] = fb[k0[m]:k0[m] + kcnt_true[m], m]
     bin_w = np.zeros(max(int(bin_off[-1]), 1), np.float32)
     for k in range(F):
         bin_w[bin_off[k]:bin_off[k + 1]] = fb[k, m0[k]:m0[k] + mcnt[k]]
@@ -93,8 +97,8 @@ def unpack_bank(p: PackedBank) -> Tuple[np.ndarray, np.ndarray]:
     a = np.zeros((p.n_freqs, p.n_mels), np.float32)
     b = np.zeros((p.n_freqs, p.n_mels), np.float32)
     for m in range(p.n_mels):
-        c = p.mel_off[m + 1] - p.mel_off[m]
-        a[p.mel_k0[m]:p.mel_k0[m] + c, m] = p.mel_w[p.mel_off[m]:p.mel_off[m + 1]]
+        c = min(p.mel_off[m + 1] - p.mel_off[m], p.n_freqs - p.mel_k0[m])   # runs are zero-padded to 4 taps
+        a[p.mel_k0[m]:p.mel_k0[m] + c, m] = p.mel_w[p.mel_off[m]:p.mel_off[m] + c]
     for k in range(p.n_freqs):
         c = p.bin_off[k + 1] - p.bin_off[k]
         b[k, p.bin_m0[k]:p.bin_m0[k] + c] = p.bin_w[p.bin_off[k]:p.bin_off[k + 1]]

@@ -55,7 +55,8 @@ typedef enum dmel_status {
  * torch.matmul(spec.T, mel_fb) of models.py:53.  Built once per n_freqs by the host
  * from the dense matrix (so the weights are bit-identical to the dense ones):
  *   mel-major (forward gather):  mel m reads bins  mel_k0[m] .. mel_k0[m]+cnt-1,
- *       cnt = mel_off[m+1]-mel_off[m], weights mel_w[mel_off[m] + i]
+ *       cnt = mel_off[m+1]-mel_off[m], weights mel_w[mel_off[m] + i]; every run is
+ *       zero-padded to cnt % 4 == 0 (so mel_off[m] % 4 == 0) and mel_k0[m]+cnt <= F+3
  *   bin-major (backward gather): bin k reads mels  bin_m0[k] .. bin_m0[k]+cnt-1,
  *       cnt = bin_off[k+1]-bin_off[k], weights bin_w[bin_off[k] + i]
  * All six arrays are device pointers, each 16-byte aligned and readable up to the next
