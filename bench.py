@@ -330,7 +330,6 @@ def main():
                 resident_step(i)
 
     sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = lib.dmel_launch_count(-1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -338,8 +337,7 @@ def main():
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches_eager = lib.dmel_launch_count(-1) - launches0
-    per_step_launches = 4   # prep + forward + backward + finalize (plus 3 driver memsets, not counted)
+    per_step_launches = 5   # prep + forward + zero-init + backward + finalize
     gpu_launches = per_step_launches * args.steps
 
     # per-kernel durations: same steps, eager, each main kernel bracketed by CUDA events on its stream
@@ -349,7 +347,7 @@ def main():
         resident_step(i)
     torch.cuda.synchronize(dev)
     kern = {}
-    for kind, name in ((0, "prep"), (1, "fwd"), (2, "bwd"), (3, "finalize")):
+    for kind, name in ((0, "prep"), (1, "fwd"), (2, "bwd"), (3, "finalize"), (4, "zero")):
         tot, cnt = ctypes.c_double(), ctypes.c_longlong()
         assert lib.dmel_profile_read(kind, ctypes.byref(tot), ctypes.byref(cnt)) == 0
         kern[name] = (tot.value / max(cnt.value, 1), cnt.value)

@@ -153,16 +153,31 @@ dmel_prep_kernel(const float* __restrict__ x, long long x_stride, int B, int N, 
         }
         // models.py:38  x[idx] - torch.mean(x[idx])
         const float* xb = x + (long long)blockIdx.x * x_stride;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int i = tid;
-        for (; i + 3 * PREP_THREADS < N; i += 4 * PREP_THREADS) {
-            s0 += __ldg(xb + i);
-            s1 += __ldg(xb + i + PREP_THREADS);
-            s2 += __ldg(xb + i + 2 * PREP_THREADS);
-            s3 += __ldg(xb + i + 3 * PREP_THREADS);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int i0 = 0;
+        if ((reinterpret_cast<uintptr_t>(xb) & 15) == 0) {
+            // 16-byte loads, 8 independent ones in flight per thread
+            const float4* x4 = reinterpret_cast<const float4*>(xb);
+            const int n4 = N >> 2;
+            int q = tid;
+            for (; q + 7 * PREP_THREADS < n4; q += 8 * PREP_THREADS) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(x4 + q + u * PREP_THREADS);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+            }
+            for (; q < n4; q += PREP_THREADS) {
+                const float4 v = __ldg(x4 + q);
+                acc[0] += (v.x + v.y) + (v.z + v.w);
+            }
+            i0 = n4 << 2;
         }
-        for (; i < N; i += PREP_THREADS) s0 += __ldg(xb + i);
-        double tot = block_sum(double(s0) + double(s1) + double(s2) + double(s3), red);
+        for (int i = i0 + tid; i < N; i += PREP_THREADS) acc[1] += __ldg(xb + i);
+        double part = 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) part += double(acc[u]);
+        double tot = block_sum(part, red);
         if (tid == 0) ws.means[blockIdx.x] = float(tot / double(N));
         return;
     }
@@ -681,9 +696,41 @@ dmel_finalize_kernel(float* __restrict__ dx, int B, int N, int chunks_per_clip, 
     if (clipsum == nullptr) return;  // DMEL_FLAG_KEEP_MEAN: no mean-removal adjoint
     const float mu = float(clipsum[b] / double(N));
     float* dxb = dx + (long long)b * N;
-    const int per = (N + chunks_per_clip - 1) / chunks_per_clip;
+    const int per = (((N + chunks_per_clip - 1) / chunks_per_clip) + 3) & ~3;
     const int lo = c * per, hi = min(N, lo + per);
-    for (int i = lo + threadIdx.x; i < hi; i += 256) dxb[i] -= mu;
+    if ((reinterpret_cast<uintptr_t>(dxb) & 15) == 0) {
+        float4* d4 = reinterpret_cast<float4*>(dxb);
+        const int q_hi = hi >> 2;
+        for (int q = (lo >> 2) + threadIdx.x; q < q_hi; q += 256) {
+            float4 v = d4[q];
+            v.x -= mu; v.y -= mu; v.z -= mu; v.w -= mu;
+            d4[q] = v;
+        }
+        for (int i = (q_hi << 2) + threadIdx.x; i < hi; i += 256) dxb[i] -= mu;
+    } else {
+        for (int i = lo + threadIdx.x; i < hi; i += 256) dxb[i] -= mu;
+    }
+}
+
+// one launch instead of three memsets: dx (halos are reduced into it), per-clip sums, dL/dlambda accumulator
+__global__ void __launch_bounds__(256)
+dmel_zero_kernel(float* __restrict__ dx, long long n_dx, double* __restrict__ clipsum, int B, WsHeader* hdr) {
+    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * 256;
+    if (gid == 0) hdr->dlam_acc = 0.0;
+    if (clipsum)
+        for (long long i = gid; i < B; i += nthreads) clipsum[i] = 0.0;
+    if (dx) {
+        if ((reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
+            float4* d4 = reinterpret_cast<float4*>(dx);
+            const long long n4 = n_dx >> 2;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (long long i = gid; i < n4; i += nthreads) d4[i] = z;
+            for (long long i = (n4 << 2) + gid; i < n_dx; i += nthreads) dx[i] = 0.f;
+        } else {
+            for (long long i = gid; i < n_dx; i += nthreads) dx[i] = 0.f;
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------
@@ -859,12 +906,15 @@ static size_t smem_bytes_fft(int L, int NG, int tw_total, int span, int sub_span
     return size_t(make_lay(L, NG, tw_total, span, sub_span, tile_words, csr_ints, csr_floats, priv_dx).total) * 4;
 }
 
-// Tile shape: NG groups x SF frames.  Pick the (NG, SF) that keeps the most warps resident per SM
-// (shared memory and a 16-warp register ceiling at <= 128 registers/thread), discounted by the
-// partial last wave over the 148 SMs; ties go to the larger tile (less halo, fewer staging passes).
+// Tile shape: NG groups x SF frames per CTA tile.  scripts/tune.py sweeps on B200 (profiles/) show a
+// flat optimum around 16 frames per tile for every transform length: smaller tiles pay the per-tile
+// fixed cost (span staging, barriers, tile IO) too often, larger ones cost occupancy and leave a
+// coarse tail over the 148 SMs.  So: TT = 16 (32 for n_fft 4096), NG = the instantiated group
+// count that keeps SF >= 4, shrunk until the tile fits shared memory or the clip.
 // DMEL_NG / DMEL_SF in the environment pin the choice (tuning experiments).
 static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int csr_ints, int csr_floats, bool bwd,
                        bool need_dx, LaunchPlan* lp) {
+    (void)B;
     const int64_t T64 = N / hop + 1;
     if (T64 > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
     const int T = int(T64);
@@ -886,51 +936,54 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
     int pin_ng = 0, pin_sf = 0;
     if (const char* e = getenv("DMEL_NG")) pin_ng = atoi(e);
     if (const char* e = getenv("DMEL_SF")) pin_sf = atoi(e);
-    const int sfs[5] = {16, 8, 4, 2, 32};
-    double best = -1.0;
-    for (int ni = 0; ni < 2; ++ni) {
-        const int NG = fi.ng[ni];
-        if (ni == 1 && NG == fi.ng[0]) break;
-        if (pin_ng && NG != pin_ng) continue;
-        for (int si = 0; si < 5; ++si) {
-            const int SF = sfs[si];
-            if (pin_sf && SF != pin_sf) continue;
-            const int TT = NG * SF;
-            if (!pin_sf && TT > 2 * T + 2 && SF > 2) continue;  // pointless: most groups would idle
-            const int64_t span64 = int64_t(TT - 1) * hop + n_fft, sub64 = int64_t(SF - 1) * hop + n_fft;
-            if (span64 > (1 << 20)) continue;
-            const size_t sm = smem_bytes_fft(n_fft, NG, fi.tw_total, int(span64), int(sub64), rows, TT, csr_ints,
-                                             csr_floats, bwd, bwd && need_dx);
-            if (sm > SMEM_MAX) continue;
-            const int warps_cta = NG * fi.gt / 32;
-            int ctas = int(SMEM_MAX / (sm + 1024));
-            ctas = std::min(ctas, std::max(1, 16 / warps_cta));
-            ctas = std::min(ctas, 32);
-            if (ctas < 1) ctas = 1;
-            const int tiles = (T + TT - 1) / TT;
-            const double total = double(B) * tiles, slots = double(NUM_SMS) * ctas;
-            const double waves = std::ceil(total / slots);
-            // useful frame slots / offered frame slots (tail tiles are partly empty) x wave fill
-            const double fill = (double(T) / (double(tiles) * TT)) * (total / (waves * slots));
-            const double score = double(ctas * warps_cta) * fill + 1e-3 * TT;
-            if (score > best) {
-                best = score;
-                lp->path = 0;
-                lp->NG = NG; lp->SF = SF; lp->TT = TT;
-                lp->span = int(span64); lp->sub_span = int(sub64);
-                lp->tiles_per_clip = tiles;
-                lp->threads = NG * fi.gt;
-                lp->smem = sm;
+    // preferred group count: one warp per transform up to 512 points -> 4 groups; 1024: 4 (bwd) / 2 (fwd)
+    int ng_pref;
+    switch (n_fft) {
+        case 1024: ng_pref = bwd ? 4 : 2; break;
+        case 2048: ng_pref = 2; break;
+        case 4096: ng_pref = 1; break;
+        default: ng_pref = 4; break;
+    }
+    int t_pow2 = 2;
+    while (t_pow2 < T) t_pow2 <<= 1;
+    int tt_target = std::min(n_fft >= 4096 ? 32 : 16, t_pow2);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        for (int ni = 0; ni < 2; ++ni) {
+            // first the preferred NG, then the other instantiated one
+            const int NG = (ni == 0) ? ng_pref : (fi.ng[0] == ng_pref ? fi.ng[1] : fi.ng[0]);
+            if (ni == 1 && NG == ng_pref) continue;
+            if (pin_ng && NG != pin_ng) continue;
+            for (int TT = tt_target; TT >= 2 * NG || TT >= 2; TT >>= 1) {
+                int SF = std::max(2, TT / NG);
+                if (pin_sf) SF = pin_sf;
+                const int tt = NG * SF;
+                const int64_t span64 = int64_t(tt - 1) * hop + n_fft, sub64 = int64_t(SF - 1) * hop + n_fft;
+                if (span64 <= (1 << 20)) {
+                    const size_t sm = smem_bytes_fft(n_fft, NG, fi.tw_total, int(span64), int(sub64), rows, tt, csr_ints,
+                                                     csr_floats, bwd, bwd && need_dx);
+                    if (sm <= SMEM_MAX) {
+                        lp->path = 0;
+                        lp->NG = NG; lp->SF = SF; lp->TT = tt;
+                        lp->span = int(span64); lp->sub_span = int(sub64);
+                        lp->tiles_per_clip = (T + tt - 1) / tt;
+                        lp->threads = NG * fi.gt;
+                        lp->smem = sm;
+                        return DMEL_OK;
+                    }
+                }
+                if (pin_sf || TT <= 2) break;
             }
         }
+        pin_ng = 0;   // a pinned shape that does not fit falls back to the automatic choice
+        pin_sf = 0;
     }
-    return best < 0 ? DMEL_ERR_SMEM_EXCEEDED : DMEL_OK;
+    return DMEL_ERR_SMEM_EXCEEDED;
 }
 
 // ---- optional instrumentation for bench.py: launch counter + per-kernel CUDA-event timing.
 // Off by default; when on, every main-kernel launch is bracketed by a pair of events recorded on
 // the launching stream (no synchronisation until dmel_profile_read).
-enum { PROF_PREP = 0, PROF_FWD = 1, PROF_BWD = 2, PROF_FINALIZE = 3, PROF_KINDS = 4 };
+enum { PROF_PREP = 0, PROF_FWD = 1, PROF_BWD = 2, PROF_FINALIZE = 3, PROF_ZERO = 4, PROF_KINDS = 5 };
 static std::atomic<long long> g_launches[PROF_KINDS];
 struct ProfState {
     bool on = false;
@@ -1237,13 +1290,14 @@ extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t
         if ((rc = run_prep(x, batch, n_points, x_row_stride, fabsf(lambda), win_length, n_fft, flags, ws, st)))
             return rc;
     }
-    // zero the accumulators (and dx: halo positions are reduced with atomics)
-    if (cudaMemsetAsync(&ws.hdr->dlam_acc, 0, sizeof(double), st) != cudaSuccess) return check_launch("memset dlam");
-    if (need_dx) {
-        if (cudaMemsetAsync(ws.clipsum, 0, size_t(batch) * sizeof(double), st) != cudaSuccess)
-            return check_launch("memset clipsum");
-        if (cudaMemsetAsync(grad_x, 0, size_t(batch) * size_t(n_points) * sizeof(float), st) != cudaSuccess)
-            return check_launch("memset grad_x");
+    // zero the accumulators (and dx: halo positions are reduced with atomics) in one launch
+    {
+        const long long n_dx = need_dx ? (long long)batch * n_points : 0;
+        long long blocks = need_dx ? (n_dx / 4 + 255) / 256 : 1;
+        blocks = std::max<long long>(1, std::min<long long>(blocks, 8LL * NUM_SMS));
+        ProfScope prof(PROF_ZERO, st);
+        dmel_zero_kernel<<<unsigned(blocks), 256, 0, st>>>(grad_x, n_dx, need_dx ? ws.clipsum : nullptr, int(batch), ws.hdr);
+        if ((rc = check_launch("dmel_zero_kernel"))) return rc;
     }
     Geom g = make_geom(batch, n_points, x_row_stride, n_fft, hop, rows, log_eps, lp);
     g.row_aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_row_stride & 3) == 0) ? 1 : 0;
@@ -1270,7 +1324,7 @@ extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t
     const float sign = lambda > 0.f ? 1.f : (lambda < 0.f ? -1.f : 0.f);
     int chunks = 1, grid = 1;
     if (need_dx) {
-        chunks = int((n_points + 8191) / 8192);
+        chunks = int((n_points + 4095) / 4096);
         grid = int(batch) * chunks;
     }
     const double* csum = (flags & DMEL_FLAG_KEEP_MEAN) ? nullptr : ws.clipsum;

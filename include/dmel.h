@@ -138,7 +138,7 @@ DMEL_API int dmel_query_launch(int64_t batch, int64_t n_points, int32_t n_fft, i
                       int32_t* smem_bytes, int32_t* threads, int32_t* path);
 
 /* Instrumentation (bench.py): cumulative number of kernels this library launched, by kind
- * (0 prep, 1 forward, 2 backward, 3 finalize, <0 all); and opt-in per-launch CUDA-event timing of
+ * (0 prep, 1 forward, 2 backward, 3 finalize, 4 zero-init, <0 all); and opt-in per-launch CUDA-event timing of
  * the calling thread's launches: enable(1) clears and starts, read() synchronises on the recorded
  * events and returns their summed duration and count, enable(0) stops and frees the events.      */
 DMEL_API long long dmel_launch_count(int32_t kind);
