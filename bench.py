@@ -451,9 +451,18 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n} of {B} clips, best of {reps} passes, fwd+bwd (dx+dlambda), torch threads={cores}"}
         print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # all ranks are done once rank 0 has printed.  Tearing the process group down while a CUDA graph with
+        # captured NCCL kernels is alive can deadlock (seen on the 2-GPU box: the line was printed, the job never
+        # exited), so synchronise and leave without running the NCCL / graph destructors.
+        torch.cuda.synchronize(dev)
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -198,6 +198,12 @@ dmel_prep_kernel(const float* __restrict__ x, long long x_stride, int B, int N, 
             sq += double(w) * double(w) * double(d * d * inv_lam3);
         }
         ws.win[n] = w;
+        if (plan.np < 0 && n < 256) {  // big-FFT path: t_hi[h] = exp(-2*pi*i*128h/n_fft), t_lo[l] = exp(-2*pi*i*l/n_fft)
+            double sn, cs;
+            const double idx = n < 128 ? 128.0 * double(n) : double(n - 128);
+            sincospi(-2.0 * idx / double(n_fft), &sn, &cs);
+            ws.tw[n] = make_float2(float(cs), float(sn));
+        }
         if (plan.np == 0) {  // direct-DFT path: plain table exp(-2*pi*i*n/n_fft)
             double sn, cs;
             sincospi(-2.0 * double(n) / double(n_fft), &sn, &cs);
@@ -341,6 +347,13 @@ __device__ __forceinline__ void span_centre(float* xs_sh, int p0, int span, int 
     }
 }
 
+// Register budget: the one-warp-per-transform kernels (L <= 512, 128-thread CTAs) are latency bound, so
+// they are compiled for DMEL_MINB_SMALL resident CTAs per SM (6 -> 80 registers, 24 warps/SM).
+#ifndef DMEL_MINB_SMALL
+#define DMEL_MINB_SMALL 1
+#endif
+__host__ __device__ constexpr int min_ctas(int L, int NG) { return (L <= 512 && NG == 4) ? DMEL_MINB_SMALL : 1; }
+
 // integer log2 of a power of two
 __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
 
@@ -348,7 +361,7 @@ __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
 // forward (persistent: each CTA stages the constant tables once and walks tiles)
 // ----------------------------------------------------------------------------
 template <int L, int NG, bool SPEC>
-__global__ void __launch_bounds__(NG * (L / Plan<L>::E))
+__global__ void __launch_bounds__(NG * (L / Plan<L>::E), min_ctas(L, NG))
 dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelDev mel,
                 const float* __restrict__ win_g, const float2* __restrict__ tw_g, const float* __restrict__ means) {
     constexpr int E = Plan<L>::E, GT = L / E, NT = NG * GT, TWN = TwTotal<L>::value;
@@ -474,7 +487,7 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
 // backward (persistent)
 // ----------------------------------------------------------------------------
 template <int L, int NG, bool SPEC, bool NEED_DX>
-__global__ void __launch_bounds__(NG * (L / Plan<L>::E))
+__global__ void __launch_bounds__(NG * (L / Plan<L>::E), min_ctas(L, NG))
 dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy,
                 float* __restrict__ dx, Geom g, MelDev mel, const float* __restrict__ win_g,
                 const float2* __restrict__ tw_g, const float* __restrict__ means, WsHeader* hdr,
@@ -534,21 +547,36 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
             // upstream gradient tile (and y when the log is fused): rows are T floats apart in HBM, so the
             // copies are 4-byte async ones, all in flight together; columns past the last frame are zero
             const long long base = (long long)b * g.M * g.T + t0;
-            for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
-                const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
-                const bool ok = tt < nfr;
-                const long long off = base + (long long)m * g.T + (ok ? tt : 0);
-                cp_async4_zfill(gt + m * TS + tt, gy + off, ok);
-                if (do_log) cp_async4_zfill(yt + m * TS + tt, y + off, ok);
+            const int q_shift = tt_shift > 2 ? tt_shift - 2 : 0;      // quads per row = TT/4 (TT >= 4), else 1
+            const int qw = g.TT >= 4 ? 4 : g.TT;
+            for (int idx = tid; idx < (g.M << q_shift); idx += NT) {
+                const int m = idx >> q_shift, tq = (idx & ((1 << q_shift) - 1)) * qw;
+                const long long off = base + (long long)m * g.T + tq;
+                float* gd = gt + m * TS + tq;
+                float* yd = yt + m * TS + tq;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (e < qw) {
+                        const bool ok = tq + e < nfr;
+                        cp_async4_zfill(gd + e, gy + off + (ok ? e : 0), ok);
+                        if (do_log) cp_async4_zfill(yd + e, y + off + (ok ? e : 0), ok);
+                    }
+                }
             }
         }
         cp_async_wait_all();
         span_centre<NT>(xs_sh, p0, g.span, g.N, mu, tid);
         if (do_log) {
             // dL/dmel = G / (mel + eps) = G * exp(-y); each thread touches the words it copied itself
-            for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
-                const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
-                gt[m * TS + tt] *= __expf(-yt[m * TS + tt]);
+            const int q_shift = tt_shift > 2 ? tt_shift - 2 : 0;
+            const int qw = g.TT >= 4 ? 4 : g.TT;
+            for (int idx = tid; idx < (g.M << q_shift); idx += NT) {
+                const int m = idx >> q_shift, tq = (idx & ((1 << q_shift) - 1)) * qw;
+                float* gd = gt + m * TS + tq;
+                const float* yd = yt + m * TS + tq;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (e < qw) gd[e] *= __expf(-yd[e]);
             }
         }
         __syncthreads();
@@ -660,12 +688,11 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
             for (int i = tid; i < span_used; i += NT) {
                 const int p = p0 + i;
                 if (p >= 0 && p < g.N) {
+                    // groups gi with 0 <= i - gi*gstep < sub_span
+                    const int gi_hi = min(NG - 1, i / gstep);
+                    const int gi_lo = max(0, (i - g.sub_span + gstep) / gstep);
                     float val = 0.f;
-#pragma unroll
-                    for (int gi = 0; gi < NG; ++gi) {
-                        const int o = i - gi * gstep;
-                        if (o >= 0 && o < g.sub_span) val += priv0[gi * lay.grp_stride + o];
-                    }
+                    for (int gi = gi_lo; gi <= gi_hi; ++gi) val += priv0[gi * lay.grp_stride + (i - gi * gstep)];
                     part += val;
                     if (p >= excl_lo && p < excl_hi) dxb[p] = val;
                     else atomicAdd(dxb + p, val);
@@ -680,6 +707,270 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
     cp_async_wait_all();
     const double tot = block_sum(double(dlam), red);
     if (tid == 0) atomicAdd(&hdr->dlam_acc, tot);
+}
+
+// ----------------------------------------------------------------------------
+// big transforms (n_fft 8192 / 16384, e.g. the 300 ms window at 44.1 kHz): one CTA per tile, the whole
+// CTA is one FFT group; the L-point spectrum buffer takes most of shared memory, so the window, the
+// signal and the sparse bank are read from global/L2 and only the tile, the two 128-entry twiddle
+// tables and (backward) the dx span live next to it
+// ----------------------------------------------------------------------------
+struct BigLay {
+    int thi, tile, priv, red, total;   // 4-byte words; buf (2L words) is at 0
+};
+__host__ __device__ inline BigLay make_big_lay(int L, int span, int tile_words, bool priv_dx) {
+    BigLay l;
+    int o = 2 * L;
+    l.thi = o;  o += 512;                     // t_hi[128] | t_lo[128] as float2
+    l.tile = o; o += round_up4(tile_words);
+    l.priv = o; o += priv_dx ? round_up4(span) : 0;
+    l.red = o;  o += 64;
+    l.total = o;
+    return l;
+}
+
+template <int L>
+__device__ __forceinline__ void big_load_pair(float2 (&v)[Plan<L>::E], const float* __restrict__ xb, const float* __restrict__ win_g,
+                                              int pa0, int hop, int N, float mu, int tid) {
+    using P0 = Pass<L, 0>;
+#pragma unroll
+    for (int i = 0; i < P0::NB; ++i) {
+        const int j = tid + i * P0::GT;
+#pragma unroll
+        for (int r = 0; r < P0::R; ++r) {
+            const int n = j + r * P0::STR;
+            const float w = __ldg(win_g + n);
+            const int pa = pa0 + n, pb = pa + hop;
+            const float xa = (pa >= 0 && pa < N) ? __ldg(xb + pa) - mu : 0.f;
+            const float xc = (pb >= 0 && pb < N) ? __ldg(xb + pb) - mu : 0.f;
+            v[i * P0::R + r] = make_float2(xa * w, xc * w);
+        }
+    }
+}
+
+template <int L, bool SPEC>
+__global__ void __launch_bounds__(L / Plan<L>::E)
+dmel_big_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelDev mel,
+                    const float* __restrict__ win_g, const float2* __restrict__ tw_g, const float* __restrict__ means) {
+    constexpr int E = Plan<L>::E, NT = L / E;
+    extern __shared__ __align__(16) float smem_f[];
+    const int TS = g.TT + 1;
+    const BigLay lay = make_big_lay(L, g.span, SPEC ? 0 : g.M * TS, false);
+    float2* buf = reinterpret_cast<float2*>(smem_f);
+    float2* t_hi = reinterpret_cast<float2*>(smem_f + lay.thi);
+    float2* t_lo = t_hi + 128;
+    float* tile = smem_f + lay.tile;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x / g.tiles_per_clip;
+    const int tile_i = blockIdx.x - b * g.tiles_per_clip;
+    const int t0 = tile_i * g.TT;
+    const int nfr = min(g.TT, g.T - t0);
+    const float* xb = x + (long long)b * g.x_stride;
+    const float mu = __ldg(means + b);
+    const bool do_log = g.log_eps >= 0.f;
+    for (int i = tid; i < 256; i += NT) t_hi[i] = __ldg(tw_g + i);
+    __syncthreads();
+
+    for (int f = 0; f < nfr; f += 2) {
+        float2 v[E];
+        big_load_pair<L>(v, xb, win_g, (t0 + f) * g.hop - L / 2, g.hop, g.N, mu, tid);
+        big_passes<L, 0, true>(v, buf, t_hi, t_lo, tid);
+        for (int k = tid; k <= L / 2; k += NT) {
+            const float2 z1 = buf[k];
+            const float2 z2 = buf[(L - k) & (L - 1)];
+            const float ar = 0.5f * (z1.x + z2.x), ai = 0.5f * (z1.y - z2.y);
+            const float br = 0.5f * (z1.y + z2.y), bi = 0.5f * (z2.x - z1.x);
+            float pa = fmaf(ar, ar, ai * ai), pb = fmaf(br, br, bi * bi);
+            if (SPEC) {
+                // (B,1,F,T): the two frames of the pair are neighbours in a row
+                float* yr = y + ((long long)b * g.M + k) * g.T + t0 + f;
+                if (do_log) { pa = __logf(pa + g.log_eps); pb = __logf(pb + g.log_eps); }
+                yr[0] = pa;
+                if (f + 1 < nfr) yr[1] = pb;
+            } else {
+                buf[k] = make_float2(pa, pb);
+            }
+        }
+        if (!SPEC) {
+            __syncthreads();
+            for (int m = tid; m < g.M; m += NT) {
+                const int k0 = __ldg(mel.mel_k0 + m);
+                const int o0 = __ldg(mel.mel_off + m), o1 = __ldg(mel.mel_off + m + 1);
+                const float2* pp = buf + k0;
+                const float4* wp = reinterpret_cast<const float4*>(mel.mel_w + o0);
+                float sa = 0.f, sb = 0.f;
+                for (int q = 0; q < ((o1 - o0) >> 2); ++q) {
+                    const float4 w = __ldg(wp + q);
+                    const float2 a0 = pp[4 * q], a1 = pp[4 * q + 1], a2 = pp[4 * q + 2], a3 = pp[4 * q + 3];
+                    sa = fmaf(w.x, a0.x, sa); sb = fmaf(w.x, a0.y, sb);
+                    sa = fmaf(w.y, a1.x, sa); sb = fmaf(w.y, a1.y, sb);
+                    sa = fmaf(w.z, a2.x, sa); sb = fmaf(w.z, a2.y, sb);
+                    sa = fmaf(w.w, a3.x, sa); sb = fmaf(w.w, a3.y, sb);
+                }
+                tile[m * TS + f] = sa;
+                tile[m * TS + f + 1] = sb;
+            }
+            // the barrier before the next scatter (inside big_passes) orders these reads of buf
+        }
+    }
+    if (!SPEC) {
+        __syncthreads();
+        float* yb = y + (long long)b * g.M * g.T + t0;
+        const int tt_shift = ilog2(g.TT);
+        for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
+            const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
+            if (tt < nfr) {
+                float val = tile[m * TS + tt];
+                if (do_log) val = __logf(val + g.log_eps);
+                yb[(long long)m * g.T + tt] = val;
+            }
+        }
+    }
+}
+
+template <int L, bool SPEC, bool NEED_DX>
+__global__ void __launch_bounds__(L / Plan<L>::E)
+dmel_big_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy,
+                    float* __restrict__ dx, Geom g, MelDev mel, const float* __restrict__ win_g,
+                    const float2* __restrict__ tw_g, const float* __restrict__ means, WsHeader* hdr,
+                    double* __restrict__ clipsum) {
+    constexpr int E = Plan<L>::E, NT = L / E, NP = Plan<L>::NP;
+    using P0 = Pass<L, 0>;
+    using PL = Pass<L, NP - 1>;
+    extern __shared__ __align__(16) float smem_f[];
+    const int TS = g.TT + 1;
+    // spectrogram mode reads dL/dy straight from global (its tile would be n_fft/2+1 rows)
+    const BigLay lay = make_big_lay(L, g.span, SPEC ? 0 : g.M * TS, NEED_DX);
+    float2* buf = reinterpret_cast<float2*>(smem_f);
+    float2* t_hi = reinterpret_cast<float2*>(smem_f + lay.thi);
+    float2* t_lo = t_hi + 128;
+    float* gt = smem_f + lay.tile;
+    float* priv = smem_f + lay.priv;
+    double* red = reinterpret_cast<double*>(smem_f + lay.red);
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x / g.tiles_per_clip;
+    const int tile_i = blockIdx.x - b * g.tiles_per_clip;
+    const int t0 = tile_i * g.TT;
+    const int nfr = min(g.TT, g.T - t0);
+    const int p0 = t0 * g.hop - L / 2;
+    const float* xb = x + (long long)b * g.x_stride;
+    const float mu = __ldg(means + b);
+    const bool do_log = g.log_eps >= 0.f;
+    const long long ybase = (long long)b * g.M * g.T + t0;
+    const float inv_lam3 = hdr->inv_lam3, cprime = hdr->cprime, centre = hdr->centre;
+
+    for (int i = tid; i < 256; i += NT) t_hi[i] = __ldg(tw_g + i);
+    if (NEED_DX)
+        for (int i = tid; i < g.span; i += NT) priv[i] = 0.f;
+    if (!SPEC) {
+        const int tt_shift = ilog2(g.TT);
+        for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
+            const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
+            float val = 0.f;
+            if (tt < nfr) {
+                const long long off = ybase + (long long)m * g.T + tt;
+                val = __ldg(gy + off);
+                if (do_log) val *= __expf(-__ldg(y + off));
+            }
+            gt[m * TS + tt] = val;
+        }
+    }
+    __syncthreads();
+
+    float dlam = 0.f;
+    for (int f = 0; f < nfr; f += 2) {
+        const bool has_b = (f + 1) < nfr;
+        const int pa0 = (t0 + f) * g.hop - L / 2;
+        float2 v[E];
+        big_load_pair<L>(v, xb, win_g, pa0, g.hop, g.N, mu, tid);
+        big_passes<L, 0, true>(v, buf, t_hi, t_lo, tid);
+        for (int k = tid; k <= L / 2; k += NT) {
+            const float2 z1 = buf[k];
+            const float2 z2 = buf[(L - k) & (L - 1)];
+            const float ar = 0.5f * (z1.x + z2.x), ai = 0.5f * (z1.y - z2.y);
+            const float br = 0.5f * (z1.y + z2.y), bi = 0.5f * (z2.x - z1.x);
+            float ga = 0.f, gb = 0.f;
+            if (SPEC) {
+                const long long off = ybase + (long long)k * g.T + f;
+                ga = __ldg(gy + off);
+                if (do_log) ga *= __expf(-__ldg(y + off));
+                if (has_b) {
+                    gb = __ldg(gy + off + 1);
+                    if (do_log) gb *= __expf(-__ldg(y + off + 1));
+                }
+            } else {
+                const int m0 = __ldg(mel.bin_m0 + k);
+                const int o0 = __ldg(mel.bin_off + k), o1 = __ldg(mel.bin_off + k + 1);
+                for (int o = o0; o < o1; ++o) {
+                    const float w = __ldg(mel.bin_w + o);
+                    const float* gp = gt + (m0 + (o - o0)) * TS + f;
+                    ga = fmaf(w, gp[0], ga);
+                    gb = fmaf(w, gp[1], gb);
+                }
+            }
+            if (k == 0 || k == L / 2) {
+                buf[k] = make_float2(2.f * ga * ar, -2.f * gb * br);
+            } else {
+                buf[k] = make_float2(ga * ar - gb * bi, -(ga * ai + gb * br));
+                buf[L - k] = make_float2(ga * ar + gb * bi, ga * ai - gb * br);
+            }
+        }
+        __syncthreads();
+        P0::gather(v, buf, tid);
+        big_passes<L, 0, false>(v, buf, t_hi, t_lo, tid);
+#pragma unroll
+        for (int i = 0; i < PL::NB; ++i) {
+#pragma unroll
+            for (int r = 0; r < PL::R; ++r) {
+                const int n = PL::out_index(tid, i, r);
+                const float2 u = v[i * PL::R + r];
+                const float w = __ldg(win_g + n);
+                const float d = float(n) - centre;
+                const float q = fmaf(d * d, inv_lam3, -cprime);
+                const int pa = pa0 + n, pb = pa + g.hop;
+                const float xa = (pa >= 0 && pa < g.N) ? __ldg(xb + pa) - mu : 0.f;
+                const float xc = (has_b && pb >= 0 && pb < g.N) ? __ldg(xb + pb) - mu : 0.f;
+                dlam = fmaf(w * q, u.x * xa - u.y * xc, dlam);
+                v[i * PL::R + r] = make_float2(u.x * w, -u.y * w);
+            }
+        }
+        if (NEED_DX) {
+            float* da = priv + f * g.hop;
+#pragma unroll
+            for (int i = 0; i < PL::NB; ++i)
+#pragma unroll
+                for (int r = 0; r < PL::R; ++r) da[PL::out_index(tid, i, r)] += v[i * PL::R + r].x;
+            __syncthreads();
+            if (has_b) {
+                float* db = da + g.hop;
+#pragma unroll
+                for (int i = 0; i < PL::NB; ++i)
+#pragma unroll
+                    for (int r = 0; r < PL::R; ++r) db[PL::out_index(tid, i, r)] += v[i * PL::R + r].y;
+            }
+            __syncthreads();
+        }
+    }
+    const double tot = block_sum(double(dlam), red);
+    if (tid == 0) atomicAdd(&hdr->dlam_acc, tot);
+    if (NEED_DX) {
+        const int span_used = (nfr - 1) * g.hop + L;
+        const int excl_lo = (tile_i == 0) ? 0 : (t0 - 1) * g.hop + L / 2;
+        const int excl_hi = (tile_i == g.tiles_per_clip - 1) ? g.N : (t0 + nfr) * g.hop - L / 2;
+        float* dxb = dx + (long long)b * g.N;
+        float part = 0.f;
+        for (int i = tid; i < span_used; i += NT) {
+            const int p = p0 + i;
+            if (p >= 0 && p < g.N) {
+                const float val = priv[i];
+                part += val;
+                if (p >= excl_lo && p < excl_hi) dxb[p] = val;
+                else atomicAdd(dxb + p, val);
+            }
+        }
+        const double cs = block_sum(double(part), red);
+        if (tid == 0) atomicAdd(clipsum + b, cs);
+    }
 }
 
 // ----------------------------------------------------------------------------
@@ -866,6 +1157,7 @@ template <int L> static PlanDesc plan_desc_of() {
 
 struct FftInfo {
     bool ok;
+    bool big;      // 8192 / 16384: one CTA per transform, tables in global memory
     int gt;        // threads per group
     int tw_total;  // twiddle table entries
     int ng[2];     // group counts per CTA that are instantiated (largest first)
@@ -885,6 +1177,8 @@ static FftInfo fft_info(int n_fft) {
         DMEL_FFT_CASE(2048, 2, 1)
         DMEL_FFT_CASE(4096, 1, 1)
 #undef DMEL_FFT_CASE
+        case 8192: f.ok = true; f.big = true; f.gt = 8192 / Plan<8192>::E; f.ng[0] = f.ng[1] = 1; f.desc.np = -1; break;
+        case 16384: f.ok = true; f.big = true; f.gt = 16384 / Plan<16384>::E; f.ng[0] = f.ng[1] = 1; f.desc.np = -1; break;
         default: f.ok = false; f.desc.np = 0; break;
     }
     return f;
@@ -932,6 +1226,26 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
         lp->smem = size_t(round_up4(n_fft)) * 4 + size_t(F) * 8 + size_t(round_up4(F) + 8) * 4 + 512;
         if (lp->smem > SMEM_MAX) return DMEL_ERR_SMEM_EXCEEDED;
         return DMEL_OK;
+    }
+    if (fi.big) {
+        // largest power-of-two tile that fits next to the L-point buffer (spectrogram mode keeps no tile)
+        const bool spec = csr_floats == 0;
+        int t_pow2 = 2;
+        while (t_pow2 < T) t_pow2 <<= 1;
+        for (int TT = std::min(16, t_pow2); TT >= 2; TT >>= 1) {
+            const int64_t span64 = int64_t(TT - 1) * hop + n_fft;
+            if (span64 > (1 << 20)) continue;
+            const size_t sm = size_t(make_big_lay(n_fft, int(span64), spec ? 0 : rows * (TT + 1), bwd && need_dx).total) * 4;
+            if (sm > SMEM_MAX) continue;
+            lp->path = 2;
+            lp->NG = 1; lp->SF = TT; lp->TT = TT;
+            lp->span = int(span64); lp->sub_span = int(span64);
+            lp->tiles_per_clip = (T + TT - 1) / TT;
+            lp->threads = fi.gt;
+            lp->smem = sm;
+            return DMEL_OK;
+        }
+        return DMEL_ERR_SMEM_EXCEEDED;
     }
     int pin_ng = 0, pin_sf = 0;
     if (const char* e = getenv("DMEL_NG")) pin_ng = atoi(e);
@@ -1090,6 +1404,45 @@ static int launch_bwd(const float* x, const float* y, const float* gy, float* dx
     }
     return dx ? launch_bwd_t<L, NG, false, true>(x, y, gy, dx, g, mel, ws, lp, st)
               : launch_bwd_t<L, NG, false, false>(x, y, gy, dx, g, mel, ws, lp, st);
+}
+
+template <int L>
+static int launch_big_fwd(const float* x, float* y, const Geom& g, const MelDev& mel, bool spec, const WsView& ws,
+                          const LaunchPlan& lp, cudaStream_t st) {
+    const unsigned grid = unsigned(int64_t(g.B) * g.tiles_per_clip);
+    int rc;
+    ProfScope prof(PROF_FWD, st);
+    if (spec) {
+        if ((rc = set_smem(dmel_big_fwd_kernel<L, true>, lp.smem))) return rc;
+        dmel_big_fwd_kernel<L, true><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means);
+    } else {
+        if ((rc = set_smem(dmel_big_fwd_kernel<L, false>, lp.smem))) return rc;
+        dmel_big_fwd_kernel<L, false><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means);
+    }
+    return check_launch("dmel_big_fwd_kernel");
+}
+
+template <int L, bool SPEC, bool NEED_DX>
+static int launch_big_bwd_t(const float* x, const float* y, const float* gy, float* dx, const Geom& g, const MelDev& mel,
+                            const WsView& ws, const LaunchPlan& lp, cudaStream_t st) {
+    const unsigned grid = unsigned(int64_t(g.B) * g.tiles_per_clip);
+    int rc;
+    if ((rc = set_smem(dmel_big_bwd_kernel<L, SPEC, NEED_DX>, lp.smem))) return rc;
+    ProfScope prof(PROF_BWD, st);
+    dmel_big_bwd_kernel<L, SPEC, NEED_DX>
+        <<<grid, lp.threads, lp.smem, st>>>(x, y, gy, dx, g, mel, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
+    return check_launch("dmel_big_bwd_kernel");
+}
+
+template <int L>
+static int launch_big_bwd(const float* x, const float* y, const float* gy, float* dx, const Geom& g, const MelDev& mel,
+                          bool spec, const WsView& ws, const LaunchPlan& lp, cudaStream_t st) {
+    if (spec) {
+        return dx ? launch_big_bwd_t<L, true, true>(x, y, gy, dx, g, mel, ws, lp, st)
+                  : launch_big_bwd_t<L, true, false>(x, y, gy, dx, g, mel, ws, lp, st);
+    }
+    return dx ? launch_big_bwd_t<L, false, true>(x, y, gy, dx, g, mel, ws, lp, st)
+              : launch_big_bwd_t<L, false, false>(x, y, gy, dx, g, mel, ws, lp, st);
 }
 
 // (n_fft, NG) -> instantiation; the NG values must match fft_info()
@@ -1261,6 +1614,10 @@ extern "C" DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t 
             x, nullptr, nullptr, y, nullptr, g, mel, spec ? 1 : 0, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
         return check_launch("dmel_dft_kernel<fwd>");
     }
+    if (lp.path == 2) {
+        return n_fft == 8192 ? launch_big_fwd<8192>(x, y, g, mel, spec, ws, lp, st)
+                             : launch_big_fwd<16384>(x, y, g, mel, spec, ws, lp, st);
+    }
 #define CALL_FWD(LL, NGG) launch_fwd<LL, NGG>(x, y, g, mel, spec, ws, lp, st)
     DMEL_DISPATCH(n_fft, lp.NG, CALL_FWD)
 #undef CALL_FWD
@@ -1315,6 +1672,10 @@ extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t
                 x, y, grad_y, nullptr, nullptr, g, mel, spec ? 1 : 0, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
         }
         if ((rc = check_launch("dmel_dft_kernel<bwd>"))) return rc;
+    } else if (lp.path == 2) {
+        rc = n_fft == 8192 ? launch_big_bwd<8192>(x, y, grad_y, grad_x, g, mel, spec, ws, lp, st)
+                           : launch_big_bwd<16384>(x, y, grad_y, grad_x, g, mel, spec, ws, lp, st);
+        if (rc) return rc;
     } else {
 #define CALL_BWD(LL, NGG) launch_bwd<LL, NGG>(x, y, grad_y, grad_x, g, mel, spec, ws, lp, st)
         DMEL_DISPATCH(n_fft, lp.NG, CALL_BWD)

@@ -110,6 +110,9 @@ template <> struct Plan<512>  { static constexpr int E = 16, NP = 3, R0 = 8,  R1
 template <> struct Plan<1024> { static constexpr int E = 16, NP = 3, R0 = 16, R1 = 8,  R2 = 8,  R3 = 1; };
 template <> struct Plan<2048> { static constexpr int E = 16, NP = 3, R0 = 16, R1 = 16, R2 = 8,  R3 = 1; };
 template <> struct Plan<4096> { static constexpr int E = 16, NP = 3, R0 = 16, R1 = 16, R2 = 16, R3 = 1; };
+// "big" plans: one CTA per transform, 32 points per thread, twiddles from two 128-entry tables
+template <> struct Plan<8192>  { static constexpr int E = 32, NP = 4, R0 = 16, R1 = 16, R2 = 8,  R3 = 4; };
+template <> struct Plan<16384> { static constexpr int E = 32, NP = 4, R0 = 16, R1 = 16, R2 = 8,  R3 = 8; };
 
 template <int L, int P> struct PlanRadix;
 template <int L> struct PlanRadix<L, 0> { static constexpr int R = Plan<L>::R0, NS = 1; };
@@ -236,6 +239,54 @@ __device__ __forceinline__ void run_passes(float2 (&v)[Plan<L>::E], float2* buf,
         group_sync<GT>(bar_id);
         Pass<L, P>::scatter(v, buf, gtid);
         group_sync<GT>(bar_id);
+    }
+}
+
+// ----------------------------------------------------------------------------
+// Big transforms (8192, 16384 points): the per-pass twiddle tables would not fit in shared
+// memory, so exp(-2*pi*i*idx/L) is formed from two 128-entry tables, idx = hi*128 + lo
+// (one extra complex multiply, two roundings).  The whole CTA is the group.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float2 tw_split(const float2* __restrict__ t_hi, const float2* __restrict__ t_lo, int idx) {
+    return cmul(t_hi[idx >> 7], t_lo[idx & 127]);
+}
+
+template <int L, int P>
+__device__ __forceinline__ void big_compute(float2 (&v)[Plan<L>::E], const float2* __restrict__ t_hi,
+                                            const float2* __restrict__ t_lo, int tid) {
+    using PS = Pass<L, P>;
+#pragma unroll
+    for (int i = 0; i < PS::NB; ++i) {
+        const int j = tid + i * PS::GT;
+        float2 t[PS::R];
+#pragma unroll
+        for (int r = 0; r < PS::R; ++r) t[r] = v[i * PS::R + r];
+        if (PS::NS > 1) {
+            const int base = (j & (PS::NS - 1)) * (L / (PS::NS * PS::R));
+#pragma unroll
+            for (int r = 1; r < PS::R; ++r) t[r] = cmul(t[r], tw_split(t_hi, t_lo, base * r));
+        }
+        RegDft<PS::R>::run(t);
+#pragma unroll
+        for (int r = 0; r < PS::R; ++r) v[i * PS::R + r] = t[r];
+    }
+}
+
+// same contract as run_passes, with __syncthreads as the group barrier
+template <int L, int P, bool STORE_LAST>
+__device__ __forceinline__ void big_passes(float2 (&v)[Plan<L>::E], float2* buf, const float2* __restrict__ t_hi,
+                                           const float2* __restrict__ t_lo, int tid) {
+    big_compute<L, P>(v, t_hi, t_lo, tid);
+    if constexpr (P + 1 < Plan<L>::NP) {
+        __syncthreads();
+        Pass<L, P>::scatter(v, buf, tid);
+        __syncthreads();
+        Pass<L, P + 1>::gather(v, buf, tid);
+        big_passes<L, P + 1, STORE_LAST>(v, buf, t_hi, t_lo, tid);
+    } else if constexpr (STORE_LAST) {
+        __syncthreads();
+        Pass<L, P>::scatter(v, buf, tid);
+        __syncthreads();
     }
 }
 

@@ -79,7 +79,7 @@ DMEL_API int dmel_abi_version(void);
 DMEL_API const char* dmel_status_string(int status);
 
 /* 1 if a kernel exists for this transform length (radix FFT path for powers of two
- * 128..4096, direct-DFT path for everything else up to DMEL_MAX_DFT_NFFT), else 0.  */
+ * 128..16384, direct-DFT path for every other even length up to DMEL_MAX_DFT_NFFT), else 0.  */
 DMEL_API int dmel_nfft_supported(int32_t n_fft);
 
 /* time_frequency.py:60-65 next_power_of_2(int(6*|lambda|)) evaluated the way the

@@ -44,6 +44,10 @@ CASES = [
     dict(name="spec_tf_N64_big_lam_norm", kind="spec", B=2, N=64, hop=1, lam=5 * 6.38, opt=False, norm=True),
     dict(name="spec_nonpow2_N100_dft", kind="spec", B=2, N=100, hop=5, lam=9.0, opt=False, norm=False),
     dict(name="spec_opt_L256", kind="spec", B=2, N=600, hop=50, lam=30.0, opt=True, norm=False),
+    # --- big transforms: 300 ms windows (search_spaces.py:29 grid at 16 / 44.1 kHz) ---
+    dict(name="mel_L8192_16k", kind="mel", B=1, N=2400, sr=16000, hop=160, M=64, lam=16000 * 0.300 / 6, opt=True, norm=False),
+    dict(name="mel_L16384_44k", kind="mel", B=1, N=4410, sr=44100, hop=441, M=128, lam=44100 * 0.300 / 6, opt=True, norm=False),
+    dict(name="spec_opt_L8192_norm", kind="spec", B=1, N=1600, hop=400, lam=-900.0, opt=True, norm=True),
 ]
 
 
@@ -74,7 +78,10 @@ def run(c, x, G, dtype, use_log):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])
     for ci, c in enumerate(CASES):
+        if only and c["name"] not in only:
+            continue
         g = torch.Generator().manual_seed(1000 + ci)
         x = torch.randn(c["B"], c["N"], generator=g, dtype=torch.float64)
         x = x + 0.3 * torch.randn(c["B"], 1, generator=g, dtype=torch.float64)  # non-zero means

@@ -102,6 +102,8 @@ def _oracle_case(dev, B, N, sr, hop, M, lam, seed, use_log=True, norm=False, opt
     (16, 8000, 8000, 80, 64, 8000 * 0.010 / 6),         # reference grid 10 ms -> n_fft 128
     (16, 8000, 8000, 80, 64, 8000 * 0.300 / 6),         # reference grid 300 ms -> n_fft 4096
     (3, 160000, 16000, 160, 128, 16000 * 0.035 / 6),    # configs[4] large-batch clip shape, n_fft 1024
+    (2, 220500, 44100, 441, 128, 44100 * 0.300 / 6),    # esc50 lambda sweep: 300 ms -> n_fft 16384 (big-FFT path)
+    (2, 160000, 16000, 160, 128, 16000 * 0.300 / 6),    # 300 ms at 16 kHz -> n_fft 8192 (big-FFT path)
 ])
 def test_matches_oracle_on_baseline_shapes(cuda_device, B, N, sr, hop, M, lam):
     (y, dx, dlam), (y0, dx0, dlam0) = _oracle_case(cuda_device, B, N, sr, hop, M, lam, seed=1234)
