@@ -49,6 +49,10 @@ def workload(name):
         return dict(B=128, N=220500, sr=44100, hop=441, M=128, lam=44100 * 0.035 / 6, n_fft=2048)
     if name == "large_batch":      # configs[4]: 8192 x 10 s @ 16 kHz over 8 GPUs = 1024 clips per GPU
         return dict(B=1024, N=160000, sr=16000, hop=160, M=128, lam=16000 * 0.035 / 6, n_fft=1024)
+    if name == "esc50_300ms":      # configs[2] lambda sweep, 300 ms window at 44.1 kHz -> n_fft 16384 (big-FFT path)
+        return dict(B=128, N=220500, sr=44100, hop=441, M=128, lam=44100 * 0.300 / 6, n_fft=16384)
+    if name == "esc50_10ms":       # configs[2] lambda sweep, 10 ms window -> n_fft 512
+        return dict(B=128, N=220500, sr=44100, hop=441, M=128, lam=44100 * 0.010 / 6, n_fft=512)
     if name.startswith("sweep_"):  # configs[3]: batch 512, n_fft 128..4096, lambda = 0.75 n_fft / 6
         n_fft = int(name.split("_")[1])
         return dict(B=512, N=8000, sr=8000, hop=80, M=64, lam=0.75 * n_fft / 6, n_fft=n_fft)

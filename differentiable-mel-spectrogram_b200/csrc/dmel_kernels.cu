@@ -348,9 +348,10 @@ __device__ __forceinline__ void span_centre(float* xs_sh, int p0, int span, int 
 }
 
 // Register budget: the one-warp-per-transform kernels (L <= 512, 128-thread CTAs) are latency bound, so
-// they are compiled for DMEL_MINB_SMALL resident CTAs per SM (6 -> 80 registers, 24 warps/SM).
+// they are compiled for DMEL_MINB_SMALL resident CTAs per SM (5 -> 96 registers, 20 warps/SM; measured
+// best of 1/5/6 on B200, gpurun_out/exp/minb.log).
 #ifndef DMEL_MINB_SMALL
-#define DMEL_MINB_SMALL 1
+#define DMEL_MINB_SMALL 5
 #endif
 __host__ __device__ constexpr int min_ctas(int L, int NG) { return (L <= 512 && NG == 4) ? DMEL_MINB_SMALL : 1; }
 
@@ -547,36 +548,21 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
             // upstream gradient tile (and y when the log is fused): rows are T floats apart in HBM, so the
             // copies are 4-byte async ones, all in flight together; columns past the last frame are zero
             const long long base = (long long)b * g.M * g.T + t0;
-            const int q_shift = tt_shift > 2 ? tt_shift - 2 : 0;      // quads per row = TT/4 (TT >= 4), else 1
-            const int qw = g.TT >= 4 ? 4 : g.TT;
-            for (int idx = tid; idx < (g.M << q_shift); idx += NT) {
-                const int m = idx >> q_shift, tq = (idx & ((1 << q_shift) - 1)) * qw;
-                const long long off = base + (long long)m * g.T + tq;
-                float* gd = gt + m * TS + tq;
-                float* yd = yt + m * TS + tq;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (e < qw) {
-                        const bool ok = tq + e < nfr;
-                        cp_async4_zfill(gd + e, gy + off + (ok ? e : 0), ok);
-                        if (do_log) cp_async4_zfill(yd + e, y + off + (ok ? e : 0), ok);
-                    }
-                }
+            for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
+                const int m = idx >> tt_shift, tt = idx & (g.TT - 1);   // consecutive lanes: consecutive frames
+                const bool ok = tt < nfr;
+                const long long off = base + (long long)m * g.T + (ok ? tt : 0);
+                cp_async4_zfill(gt + m * TS + tt, gy + off, ok);
+                if (do_log) cp_async4_zfill(yt + m * TS + tt, y + off, ok);
             }
         }
         cp_async_wait_all();
         span_centre<NT>(xs_sh, p0, g.span, g.N, mu, tid);
         if (do_log) {
             // dL/dmel = G / (mel + eps) = G * exp(-y); each thread touches the words it copied itself
-            const int q_shift = tt_shift > 2 ? tt_shift - 2 : 0;
-            const int qw = g.TT >= 4 ? 4 : g.TT;
-            for (int idx = tid; idx < (g.M << q_shift); idx += NT) {
-                const int m = idx >> q_shift, tq = (idx & ((1 << q_shift) - 1)) * qw;
-                float* gd = gt + m * TS + tq;
-                const float* yd = yt + m * TS + tq;
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (e < qw) gd[e] *= __expf(-yd[e]);
+            for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
+                const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
+                gt[m * TS + tt] *= __expf(-yt[m * TS + tt]);
             }
         }
         __syncthreads();
@@ -688,11 +674,13 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
             for (int i = tid; i < span_used; i += NT) {
                 const int p = p0 + i;
                 if (p >= 0 && p < g.N) {
-                    // groups gi with 0 <= i - gi*gstep < sub_span
-                    const int gi_hi = min(NG - 1, i / gstep);
-                    const int gi_lo = max(0, (i - g.sub_span + gstep) / gstep);
+                    // groups gi whose sub-span covers i: 0 <= i - gi*gstep < sub_span (one unsigned compare each)
                     float val = 0.f;
-                    for (int gi = gi_lo; gi <= gi_hi; ++gi) val += priv0[gi * lay.grp_stride + (i - gi * gstep)];
+#pragma unroll
+                    for (int gi = 0; gi < NG; ++gi) {
+                        const int o = i - gi * gstep;
+                        if (unsigned(o) < unsigned(g.sub_span)) val += priv0[gi * lay.grp_stride + o];
+                    }
                     part += val;
                     if (p >= excl_lo && p < excl_hi) dxb[p] = val;
                     else atomicAdd(dxb + p, val);

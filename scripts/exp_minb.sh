@@ -4,9 +4,7 @@ set -u
 mkdir -p gpurun_out/exp
 for MB in 1 5 6; do
   make -B -C differentiable-mel-spectrogram_b200/csrc EXTRA=-DDMEL_MINB_SMALL=$MB > /dev/null 2>&1
-  for SF in 2 4; do
-    echo "== MINB=$MB SF=$SF"
-    DMEL_ONLY_NG=4 DMEL_ONLY_SF=$SF python scripts/tune.py audio_mnist sweep_128 sweep_256 2>&1 | grep -E '"ng": 4, "sf": '$SF','
-  done
+  echo "== MINB=$MB"
+  python scripts/tune.py ${@:-audio_mnist} 2>&1 | grep -E '"ng": 4, "sf": (2|4),'
 done 2>&1 | tee gpurun_out/exp/minb.log
 make -B -C differentiable-mel-spectrogram_b200/csrc > /dev/null 2>&1

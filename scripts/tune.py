@@ -13,6 +13,10 @@ import dmel_b200 as dm
 from importlib import import_module
 
 
+def geo_big(w):
+    return w["n_fft"] >= 8192
+
+
 def run(wname, steps=30):
     w = bench.workload(wname)
     dev = torch.device("cuda:0")
@@ -20,6 +24,8 @@ def run(wname, steps=30):
     B, N, sr, hop, M, lam = w["B"], w["N"], w["sr"], w["hop"], w["M"], w["lam"]
     if wname == "large_batch":
         B = 256
+    if geo_big(w):
+        B = 16
     T = N // hop + 1
     geo = dm.resolve_geometry(B, N, hop, lam, True, M)
     bank = import_module("differentiable-mel-spectrogram_b200.melbank").device_bank(geo.n_freqs, 0.0, sr // 2, M, sr, dev)
@@ -33,10 +39,11 @@ def run(wname, steps=30):
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     st = int(torch.cuda.current_stream(dev).cuda_stream)
     res = []
-    ngs = {128: (8, 4), 256: (8, 4), 512: (8, 4), 1024: (4, 2), 2048: (2, 1), 4096: (1,)}[geo.n_fft]
+    ngs = {128: (8, 4), 256: (8, 4), 512: (8, 4), 1024: (4, 2), 2048: (2, 1), 4096: (1,), 8192: (1,), 16384: (1,)}[geo.n_fft]
     for ng in ngs:
-        for sf in (2, 4, 8, 16, 32):
-            os.environ["DMEL_NG"], os.environ["DMEL_SF"] = str(ng), str(sf)
+        for sf in ((0,) if geo_big(w) else (2, 4, 8, 16, 32)):
+            if sf:
+                os.environ["DMEL_NG"], os.environ["DMEL_SF"] = str(ng), str(sf)
             def step(i, need_dx=True):
                 rc = lib.dmel_forward_f32(xs[i % R].data_ptr(), B, N, N, lam, geo.win_length, geo.n_fft, hop, M, bank.ref(), 1e-10, 0,
                                           y.data_ptr(), ws.data_ptr(), wsb, st)
@@ -62,7 +69,7 @@ def run(wname, steps=30):
                 lib.dmel_profile_enable(0)
             res.append(out)
             print(wname, json.dumps(out), flush=True)
-    os.environ.pop("DMEL_NG"); os.environ.pop("DMEL_SF")
+    os.environ.pop("DMEL_NG", None); os.environ.pop("DMEL_SF", None)
     return res
 
 
