@@ -353,7 +353,10 @@ __device__ __forceinline__ void span_centre(float* xs_sh, int p0, int span, int 
 #ifndef DMEL_MINB_SMALL
 #define DMEL_MINB_SMALL 5
 #endif
-__host__ __device__ constexpr int min_ctas(int L, int NG) { return (L <= 512 && NG == 4) ? DMEL_MINB_SMALL : 1; }
+// Everything else keeps the 128-register budget (512 threads' worth of CTAs per SM).
+__host__ __device__ constexpr int min_ctas(int L, int NG, int NT) {
+    return (L <= 512 && NG == 4) ? DMEL_MINB_SMALL : (512 / NT > 0 ? 512 / NT : 1);
+}
 
 // integer log2 of a power of two
 __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
@@ -362,7 +365,7 @@ __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
 // forward (persistent: each CTA stages the constant tables once and walks tiles)
 // ----------------------------------------------------------------------------
 template <int L, int NG, bool SPEC>
-__global__ void __launch_bounds__(NG * (L / Plan<L>::E), min_ctas(L, NG))
+__global__ void __launch_bounds__(NG * (L / Plan<L>::E), min_ctas(L, NG, NG * (L / Plan<L>::E)))
 dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelDev mel,
                 const float* __restrict__ win_g, const float2* __restrict__ tw_g, const float* __restrict__ means) {
     constexpr int E = Plan<L>::E, GT = L / E, NT = NG * GT, TWN = TwTotal<L>::value;
@@ -488,7 +491,7 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
 // backward (persistent)
 // ----------------------------------------------------------------------------
 template <int L, int NG, bool SPEC, bool NEED_DX>
-__global__ void __launch_bounds__(NG * (L / Plan<L>::E), min_ctas(L, NG))
+__global__ void __launch_bounds__(NG * (L / Plan<L>::E), min_ctas(L, NG, NG * (L / Plan<L>::E)))
 dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy,
                 float* __restrict__ dx, Geom g, MelDev mel, const float* __restrict__ win_g,
                 const float2* __restrict__ tw_g, const float* __restrict__ means, WsHeader* hdr,
@@ -1189,10 +1192,10 @@ static size_t smem_bytes_fft(int L, int NG, int tw_total, int span, int sub_span
 }
 
 // Tile shape: NG groups x SF frames per CTA tile.  scripts/tune.py sweeps on B200 (profiles/) show a
-// flat optimum around 16 frames per tile for every transform length: smaller tiles pay the per-tile
-// fixed cost (span staging, barriers, tile IO) too often, larger ones cost occupancy and leave a
-// coarse tail over the 148 SMs.  So: TT = 16 (32 for n_fft 4096), NG = the instantiated group
-// count that keeps SF >= 4, shrunk until the tile fits shared memory or the clip.
+// flat optimum around 8-16 frames per tile: smaller tiles pay the per-tile fixed cost (span staging,
+// barriers, tile IO) too often, larger ones cost occupancy and leave a coarse tail over the 148 SMs.
+// The preferred (groups, frames per group) per transform length is tabulated below and shrunk
+// until the tile fits shared memory or the clip.
 // DMEL_NG / DMEL_SF in the environment pin the choice (tuning experiments).
 static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int csr_ints, int csr_floats, bool bwd,
                        bool need_dx, LaunchPlan* lp) {
@@ -1238,26 +1241,24 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
     int pin_ng = 0, pin_sf = 0;
     if (const char* e = getenv("DMEL_NG")) pin_ng = atoi(e);
     if (const char* e = getenv("DMEL_SF")) pin_sf = atoi(e);
-    // preferred group count: one warp per transform up to 512 points -> 4 groups; 1024: 4 (bwd) / 2 (fwd)
-    int ng_pref;
+    // measured optima (scripts/tune.py on B200, profiles/*tune*.log): (groups, frames per group)
+    int ng_pref, sf_pref;
     switch (n_fft) {
-        case 1024: ng_pref = bwd ? 4 : 2; break;
-        case 2048: ng_pref = 2; break;
-        case 4096: ng_pref = 1; break;
-        default: ng_pref = 4; break;
+        case 1024: ng_pref = 2; sf_pref = 8; break;
+        case 2048: ng_pref = 1; sf_pref = 8; break;
+        case 4096: ng_pref = 1; sf_pref = 32; break;
+        default: ng_pref = 4; sf_pref = 4; break;    // one warp per transform
     }
-    int t_pow2 = 2;
-    while (t_pow2 < T) t_pow2 <<= 1;
-    int tt_target = std::min(n_fft >= 4096 ? 32 : 16, t_pow2);
     for (int attempt = 0; attempt < 2; ++attempt) {
         for (int ni = 0; ni < 2; ++ni) {
             // first the preferred NG, then the other instantiated one
             const int NG = (ni == 0) ? ng_pref : (fi.ng[0] == ng_pref ? fi.ng[1] : fi.ng[0]);
             if (ni == 1 && NG == ng_pref) continue;
             if (pin_ng && NG != pin_ng) continue;
-            for (int TT = tt_target; TT >= 2 * NG || TT >= 2; TT >>= 1) {
-                int SF = std::max(2, TT / NG);
-                if (pin_sf) SF = pin_sf;
+            int sf0 = pin_sf ? pin_sf : sf_pref;
+            // no point in a tile much longer than the clip
+            while (!pin_sf && sf0 > 2 && NG * (sf0 / 2) >= T) sf0 >>= 1;
+            for (int SF = sf0; SF >= 2; SF >>= 1) {
                 const int tt = NG * SF;
                 const int64_t span64 = int64_t(tt - 1) * hop + n_fft, sub64 = int64_t(SF - 1) * hop + n_fft;
                 if (span64 <= (1 << 20)) {
@@ -1273,7 +1274,7 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
                         return DMEL_OK;
                     }
                 }
-                if (pin_sf || TT <= 2) break;
+                if (pin_sf) break;
             }
         }
         pin_ng = 0;   // a pinned shape that does not fit falls back to the automatic choice
