@@ -74,7 +74,25 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
 
 
 def _stream_ptr(device: torch.device) -> int:
-    return int(torch.cuda.current_stream(device).cuda_stream)
+    # raw cudaStream_t of torch's current stream on that device (no Stream object construction)
+    return int(torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device()))
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already current (saves two driver calls per launch)."""
+
+    def __init__(self, dev: torch.device):
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self._ctx = None if idx == torch.cuda.current_device() else torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self._ctx is not None:
+            self._ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+        return False
 
 
 class DmelFunction(torch.autograd.Function):
@@ -89,7 +107,7 @@ class DmelFunction(torch.autograd.Function):
         y = torch.empty((geo.batch, 1, geo.rows, geo.n_frames), dtype=torch.float32, device=dev)
         ws_bytes = lib.dmel_workspace_bytes(geo.batch, geo.n_fft)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             rc = lib.dmel_forward_f32(
                 x.data_ptr(), geo.batch, geo.n_points, x.stride(0),
                 lam_value, geo.win_length, geo.n_fft, geo.hop,
@@ -120,7 +138,7 @@ class DmelFunction(torch.autograd.Function):
         grad_x = torch.empty((geo.batch, geo.n_points), dtype=torch.float32, device=dev) if need_dx else None
         grad_lambda = torch.empty((), dtype=torch.float32, device=dev)
         ws = ctx.ws
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             rc = lib.dmel_backward_f32(
                 x.data_ptr(), geo.batch, geo.n_points, x.stride(0),
                 ctx.lam_value, geo.win_length, geo.n_fft, geo.hop,
