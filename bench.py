@@ -43,6 +43,8 @@ L2_BYTES = 126 * 1024 * 1024
 
 def workload(name):
     """BASELINE.json configs -> concrete synthetic shapes. B is the per-GPU batch."""
+    if name == "tiny":             # CI-sized case (tests/test_bench_cli.py); not a BASELINE config
+        return dict(B=4, N=1600, sr=8000, hop=80, M=16, lam=8000 * 0.035 / 6, n_fft=512)
     if name == "audio_mnist":      # configs[1]: 1 s clips, batch 256, n_fft 512, 64 mels
         return dict(B=256, N=8000, sr=8000, hop=80, M=64, lam=8000 * 0.035 / 6, n_fft=512)
     if name == "esc50":            # configs[2]: 5 s @ 44.1 kHz, batch 128, n_fft 2048, 128 mels
@@ -357,6 +359,24 @@ def main():
         kern[name] = (tot.value / max(cnt.value, 1), cnt.value)
     lib.dmel_profile_enable(0)
 
+    # training mode of the reference (x is data, only lambd trains): backward without dL/dx
+    def lambda_only_step(i):
+        s = i % R
+        st = int(torch.cuda.current_stream(dev).cuda_stream)
+        lib.dmel_forward_f32(xs[s].data_ptr(), B, N, N, lam, geo.win_length, geo.n_fft, hop, M, bank.ref(), LOG_EPS, 0,
+                             ys[s].data_ptr(), wss[s].data_ptr(), ws_bytes, st)
+        lib.dmel_backward_f32(xs[s].data_ptr(), B, N, N, lam, geo.win_length, geo.n_fft, hop, M, bank.ref(), LOG_EPS, 0,
+                              ys[s].data_ptr(), Gs[s].data_ptr(), None, dls[s].data_ptr(), wss[s].data_ptr(), ws_bytes, 1, st)
+    for i in range(3):
+        lambda_only_step(i)
+    torch.cuda.synchronize(dev)
+    ev0.record()
+    for i in range(kprof_steps):
+        lambda_only_step(i)
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    ms_lambda_only = ev0.elapsed_time(ev1) / kprof_steps
+
     # ---- e2e through the public module from pinned host memory ----
     e2e = None
     if not args.no_e2e:
@@ -439,6 +459,9 @@ def main():
                 "collective": "nccl all_reduce(dL/dlambda, 1 x fp32) per step" if world > 1 else "none (1 GPU)"}),
             "gpu_launches": gpu_launches,
             "kernels_ms": {k: round(v[0], 6) for k, v in kern.items()},
+            "lambda_only": {"ms_per_step": ms_lambda_only, "value": audio_s / (ms_lambda_only * 1e-3), "unit": UNIT,
+                            "note": "per GPU, eager launches: forward + backward with dL/dlambda only (x without grad, the "
+                                    "reference's training case, models.py:19 / main.py:27)"},
             "roofline": {"bound": "hbm", "kernel": f"dmel_{dom}_kernel<{w['n_fft']}>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algorithmic_bytes(w, dom),
