@@ -89,7 +89,6 @@ struct Geom {
     int TT;                      // frames per CTA tile (= NG * SF)
     int SF;                      // frames per group sub-tile (even)
     int tiles_per_clip, span;    // span = (TT-1)*hop + n_fft samples staged per tile
-    int quota;                   // frames per persistent CTA (even); CTA c owns batch frames [c*quota, (c+1)*quota)
     int sub_span;                // (SF-1)*hop + n_fft: private dx span of one group
     int csr_ints, csr_floats;    // size of the sparse-bank form the kernel stages (0 in spectrogram mode)
     long long x_stride;
@@ -400,29 +399,24 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
     const int* s_k0 = csr_i;
     const int* s_off = csr_i + round_up4(g.M);
 
-    // this CTA's contiguous range of the batch's frames (frame F = b*T + t); tiles never cross a clip
-    const long long total_frames = (long long)g.B * g.T;
-    const long long F_end = min(total_frames, (long long)(blockIdx.x + 1) * g.quota);
-    for (long long Fcur = (long long)blockIdx.x * g.quota; Fcur < F_end;) {
-        const int b = int(Fcur / g.T);
-        const int t0 = int(Fcur - (long long)b * g.T);
-        const int nfr = int(min((long long)min(g.TT, g.T - t0), F_end - Fcur));
-        Fcur += nfr;
-        // frames per group in this tile: spread a short tile over all groups (even, <= SF)
-        const int sf = min(g.SF, max(2, (((nfr + NG - 1) / NG) + 1) & ~1));
+    const int total_tiles = g.B * g.tiles_per_clip;
+    for (int tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
+        const int b = tix / g.tiles_per_clip;
+        const int tile_i = tix - b * g.tiles_per_clip;
+        const int t0 = tile_i * g.TT;
+        const int nfr = min(g.TT, g.T - t0);
         const int p0 = t0 * g.hop - L / 2;
         const float* xb = x + (long long)b * g.x_stride;
         const float* xs = xs_sh + (p0 & 3);
-        const int span_t = (nfr - 1 + (nfr & 1)) * g.hop + L;      // samples this tile really touches
 
-        span_issue<NT>(xs_sh, xb, p0, span_t, g.N, row_aligned, tid);
+        span_issue<NT>(xs_sh, xb, p0, g.span, g.N, row_aligned, tid);
         const float mu = __ldg(means + b);
         cp_async_wait_all();
-        span_centre<NT>(xs_sh, p0, span_t, g.N, mu, tid);
+        span_centre<NT>(xs_sh, p0, g.span, g.N, mu, tid);
         __syncthreads();
 
-        const int f_hi = min(grp * sf + sf, nfr);
-        for (int f = grp * sf; f < f_hi; f += 2) {
+        const int f_hi = min(grp * g.SF + g.SF, nfr);
+        for (int f = grp * g.SF; f < f_hi; f += 2) {
             const float* xa = xs + f * g.hop;
             const float* xb2 = xa + g.hop;
             float2 v[E];
@@ -539,22 +533,17 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
     const float inv_lam3 = hdr->inv_lam3, cprime = hdr->cprime, centre = hdr->centre;
     float dlam = 0.f;
 
-    // this CTA's contiguous range of the batch's frames (frame F = b*T + t); tiles never cross a clip
-    const long long total_frames = (long long)g.B * g.T;
-    const long long F_end = min(total_frames, (long long)(blockIdx.x + 1) * g.quota);
-    for (long long Fcur = (long long)blockIdx.x * g.quota; Fcur < F_end;) {
-        const int b = int(Fcur / g.T);
-        const int t0 = int(Fcur - (long long)b * g.T);
-        const int nfr = int(min((long long)min(g.TT, g.T - t0), F_end - Fcur));
-        Fcur += nfr;
-        // frames per group in this tile: spread a short tile over all groups (even, <= SF)
-        const int sf = min(g.SF, max(2, (((nfr + NG - 1) / NG) + 1) & ~1));
+    const int total_tiles = g.B * g.tiles_per_clip;
+    for (int tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
+        const int b = tix / g.tiles_per_clip;
+        const int tile_i = tix - b * g.tiles_per_clip;
+        const int t0 = tile_i * g.TT;
+        const int nfr = min(g.TT, g.T - t0);
         const int p0 = t0 * g.hop - L / 2;
         const float* xb = x + (long long)b * g.x_stride;
         const float* xs = xs_sh + (p0 & 3);
-        const int span_t = (nfr - 1 + (nfr & 1)) * g.hop + L;      // samples this tile really touches
 
-        span_issue<NT>(xs_sh, xb, p0, span_t, g.N, row_aligned, tid);
+        span_issue<NT>(xs_sh, xb, p0, g.span, g.N, row_aligned, tid);
         const float mu = __ldg(means + b);
         if (NEED_DX)
             for (int i = gtid; i < g.sub_span; i += GT) priv[i] = 0.f;
@@ -571,7 +560,7 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
             }
         }
         cp_async_wait_all();
-        span_centre<NT>(xs_sh, p0, span_t, g.N, mu, tid);
+        span_centre<NT>(xs_sh, p0, g.span, g.N, mu, tid);
         if (do_log) {
             // dL/dmel = G / (mel + eps) = G * exp(-y); each thread touches the words it copied itself
             for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
@@ -581,8 +570,8 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
         }
         __syncthreads();
 
-        const int f_lo = grp * sf;
-        const int f_hi = min(f_lo + sf, nfr);
+        const int f_lo = grp * g.SF;
+        const int f_hi = min(f_lo + g.SF, nfr);
         for (int f = f_lo; f < f_hi; f += 2) {
             const float* xa = xs + f * g.hop;
             const float* xb2 = xa + g.hop;
@@ -679,12 +668,11 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
             // merge the groups' sub-spans; crop the centre padding; positions no other tile touches are
             // stored, the halos shared with the neighbouring tiles are reduced into the zeroed dx
             const int span_used = (nfr - 1) * g.hop + L;
-            // the neighbouring tiles of the clip hold frames t0-1 and t0+nfr, whoever owns them
-            const int excl_lo = (t0 == 0) ? 0 : (t0 - 1) * g.hop + L / 2;
-            const int excl_hi = (t0 + nfr == g.T) ? g.N : (t0 + nfr) * g.hop - L / 2;
+            const int excl_lo = (tile_i == 0) ? 0 : (t0 - 1) * g.hop + L / 2;
+            const int excl_hi = (tile_i == g.tiles_per_clip - 1) ? g.N : (t0 + nfr) * g.hop - L / 2;
             float* dxb = dx + (long long)b * g.N;
             const float* priv0 = smem_f + lay.grp + 2 * L;
-            const int gstep = sf * g.hop;
+            const int gstep = g.SF * g.hop;
             float part = 0.f;
             for (int i = tid; i < span_used; i += NT) {
                 const int p = p0 + i;
@@ -1350,9 +1338,7 @@ static int set_smem(K kernel, size_t smem) {
     return DMEL_OK;
 }
 
-// persistent launch: at most one resident wave of CTAs (occupancy x SM count); the batch's B*T frames are dealt
-// out in equal contiguous ranges (`quota` frames per CTA, even), so there is no partial last wave and no
-// half-empty last tile per clip
+// persistent launch: one resident wave of CTAs (occupancy x SM count), each walking tiles with stride gridDim
 template <typename K>
 static unsigned persistent_grid(K kernel, const LaunchPlan& lp, int64_t total_tiles) {
     int per_sm = 0;
@@ -1369,28 +1355,14 @@ static unsigned persistent_grid(K kernel, const LaunchPlan& lp, int64_t total_ti
     return unsigned(std::min<int64_t>(total_tiles, cap));
 }
 
-// frames per CTA: equal shares of B*T over `slots` CTAs, rounded up to whole tiles when a CTA gets many of
-// them (the rounding is then negligible) and to an even count otherwise; returns the grid that covers B*T
-static unsigned frame_partition(unsigned slots, Geom* g) {
-    const long long total = (long long)g->B * g->T;
-    long long q = (total + slots - 1) / slots;
-    if (q >= 8LL * g->TT) q = (q + g->TT - 1) / g->TT * g->TT;
-    else q = (q + 1) & ~1LL;
-    if (q < 2) q = 2;
-    if (q > INT32_MAX / 2) q = INT32_MAX / 2;
-    g->quota = int(q);
-    return unsigned((total + q - 1) / q);
-}
-
 template <int L, int NG, bool SPEC>
 static int launch_fwd_t(const float* x, float* y, const Geom& g, const MelDev& mel, const WsView& ws,
                         const LaunchPlan& lp, cudaStream_t st) {
     int rc;
     if ((rc = set_smem(dmel_fwd_kernel<L, NG, SPEC>, lp.smem))) return rc;
-    Geom gq = g;
-    const unsigned grid = frame_partition(persistent_grid(dmel_fwd_kernel<L, NG, SPEC>, lp, int64_t(g.B) * g.tiles_per_clip), &gq);
+    const unsigned grid = persistent_grid(dmel_fwd_kernel<L, NG, SPEC>, lp, int64_t(g.B) * g.tiles_per_clip);
     ProfScope prof(PROF_FWD, st);
-    dmel_fwd_kernel<L, NG, SPEC><<<grid, lp.threads, lp.smem, st>>>(x, y, gq, mel, ws.win, ws.tw, ws.means);
+    dmel_fwd_kernel<L, NG, SPEC><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means);
     return check_launch("dmel_fwd_kernel");
 }
 
@@ -1399,12 +1371,10 @@ static int launch_bwd_t(const float* x, const float* y, const float* gy, float* 
                         const WsView& ws, const LaunchPlan& lp, cudaStream_t st) {
     int rc;
     if ((rc = set_smem(dmel_bwd_kernel<L, NG, SPEC, NEED_DX>, lp.smem))) return rc;
-    Geom gq = g;
-    const unsigned grid =
-        frame_partition(persistent_grid(dmel_bwd_kernel<L, NG, SPEC, NEED_DX>, lp, int64_t(g.B) * g.tiles_per_clip), &gq);
+    const unsigned grid = persistent_grid(dmel_bwd_kernel<L, NG, SPEC, NEED_DX>, lp, int64_t(g.B) * g.tiles_per_clip);
     ProfScope prof(PROF_BWD, st);
     dmel_bwd_kernel<L, NG, SPEC, NEED_DX>
-        <<<grid, lp.threads, lp.smem, st>>>(x, y, gy, dx, gq, mel, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
+        <<<grid, lp.threads, lp.smem, st>>>(x, y, gy, dx, g, mel, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
     return check_launch("dmel_bwd_kernel");
 }
 
