@@ -94,6 +94,7 @@ struct Geom {
     long long x_stride;
     float log_eps;
     int row_aligned;             // x and x_stride are 16-byte aligned: spans may move as 16-byte quads
+    int lookahead;               // 1: span (and dL/dy, y) buffers are doubled and tile i+1 is prefetched during tile i
 };
 
 struct MelDev {
@@ -260,12 +261,12 @@ struct SmemLay {
 };
 
 __host__ __device__ inline SmemLay make_lay(int L, int NG, int tw_total, int span, int sub_span, int tile_words,
-                                            int csr_ints, int csr_floats, bool priv_dx) {
+                                            int csr_ints, int csr_floats, bool priv_dx, int span_bufs) {
     SmemLay l;
     int o = 0;
     l.twt = o;   o += round_up4(2 * tw_total);
     l.win = o;   o += L;
-    l.xs = o;    o += round_up4(span + 4);   // + up to 3 words of 16-byte phase shift
+    l.xs = o;    o += span_bufs * round_up4(span + 4);   // (+ up to 3 words of 16-byte phase shift each)
     l.tile = o;  o += round_up4(tile_words);
     l.csr_i = o; o += round_up4(csr_ints);
     l.csr_w = o; o += round_up4(csr_floats);
@@ -372,7 +373,7 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
     using P0 = Pass<L, 0>;
     extern __shared__ __align__(16) float smem_f[];
     const int TS = g.TT + 1;
-    const SmemLay lay = make_lay(L, NG, TWN, g.span, g.sub_span, g.M * TS, g.csr_ints, g.csr_floats, false);
+    const SmemLay lay = make_lay(L, NG, TWN, g.span, g.sub_span, g.M * TS, g.csr_ints, g.csr_floats, false, 1 + g.lookahead);
     float2* twt = reinterpret_cast<float2*>(smem_f + lay.twt);
     float* win = smem_f + lay.win;
     float* xs_sh = smem_f + lay.xs;
@@ -399,21 +400,40 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
     const int* s_k0 = csr_i;
     const int* s_off = csr_i + round_up4(g.M);
 
+    // Persistent tile loop with a one-tile look-ahead: while tile i is transformed, the span of tile i+1 is
+    // already landing in the other span buffer (cp.async), so the staging latency is off the critical path.
     const int total_tiles = g.B * g.tiles_per_clip;
-    for (int tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
+    const int xs_words = round_up4(g.span + 4);
+    const bool ahead = g.lookahead != 0;
+    if (ahead && int(blockIdx.x) < total_tiles) {
+        const int b0 = blockIdx.x / g.tiles_per_clip;
+        const int p00 = (blockIdx.x - b0 * g.tiles_per_clip) * g.TT * g.hop - L / 2;
+        span_issue<NT>(xs_sh, x + (long long)b0 * g.x_stride, p00, g.span, g.N, row_aligned, tid);
+    }
+    int it = 0;
+    for (int tix = blockIdx.x; tix < total_tiles; tix += gridDim.x, ++it) {
         const int b = tix / g.tiles_per_clip;
         const int tile_i = tix - b * g.tiles_per_clip;
         const int t0 = tile_i * g.TT;
         const int nfr = min(g.TT, g.T - t0);
         const int p0 = t0 * g.hop - L / 2;
-        const float* xb = x + (long long)b * g.x_stride;
-        const float* xs = xs_sh + (p0 & 3);
+        float* xs_cur = xs_sh + (ahead ? (it & 1) * xs_words : 0);
+        const float* xs = xs_cur + (p0 & 3);
 
-        span_issue<NT>(xs_sh, xb, p0, g.span, g.N, row_aligned, tid);
+        if (!ahead) span_issue<NT>(xs_cur, x + (long long)b * g.x_stride, p0, g.span, g.N, row_aligned, tid);
         const float mu = __ldg(means + b);
         cp_async_wait_all();
-        span_centre<NT>(xs_sh, p0, g.span, g.N, mu, tid);
-        __syncthreads();
+        span_centre<NT>(xs_cur, p0, g.span, g.N, mu, tid);
+        __syncthreads();   // also: every warp is done with the previous tile (its span buffer, the output tile)
+        if (ahead) {
+            const int nx = tix + gridDim.x;
+            if (nx < total_tiles) {
+                const int bn = nx / g.tiles_per_clip;
+                const int pn = (nx - bn * g.tiles_per_clip) * g.TT * g.hop - L / 2;
+                span_issue<NT>(xs_sh + ((it + 1) & 1) * xs_words, x + (long long)bn * g.x_stride, pn, g.span, g.N,
+                               row_aligned, tid);
+            }
+        }
 
         const int f_hi = min(grp * g.SF + g.SF, nfr);
         for (int f = grp * g.SF; f < f_hi; f += 2) {
@@ -502,12 +522,12 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
     using PL = Pass<L, NP - 1>;
     extern __shared__ __align__(16) float smem_f[];
     const int TS = g.TT + 1;
-    const SmemLay lay = make_lay(L, NG, TWN, g.span, g.sub_span, 2 * round_up4(g.M * TS), g.csr_ints, g.csr_floats, NEED_DX);
+    const SmemLay lay = make_lay(L, NG, TWN, g.span, g.sub_span, (2 + 2 * g.lookahead) * round_up4(g.M * TS), g.csr_ints,
+                                 g.csr_floats, NEED_DX, 1 + g.lookahead);
     float2* twt = reinterpret_cast<float2*>(smem_f + lay.twt);
     float* win = smem_f + lay.win;
     float* xs_sh = smem_f + lay.xs;
     float* gt = smem_f + lay.tile;
-    float* yt = gt + round_up4(g.M * TS);   // raw y tile (fused log only)
     int* csr_i = reinterpret_cast<int*>(smem_f + lay.csr_i);
     float* csr_w = smem_f + lay.csr_w;
     double* red = reinterpret_cast<double*>(smem_f + lay.red);
@@ -533,42 +553,60 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
     const float inv_lam3 = hdr->inv_lam3, cprime = hdr->cprime, centre = hdr->centre;
     float dlam = 0.f;
 
+    // Persistent tile loop with a one-tile look-ahead (see the forward kernel): the span and the dL/dy / y
+    // tiles of tile i+1 land in the alternate buffers while tile i is processed.
     const int total_tiles = g.B * g.tiles_per_clip;
-    for (int tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
+    const int xs_words = round_up4(g.span + 4);
+    const int tile_words = round_up4(g.M * TS);
+    auto issue_tile = [&](int tix_, int slot) {
+        const int b_ = tix_ / g.tiles_per_clip;
+        const int t0_ = (tix_ - b_ * g.tiles_per_clip) * g.TT;
+        const int nfr_ = min(g.TT, g.T - t0_);
+        span_issue<NT>(xs_sh + slot * xs_words, x + (long long)b_ * g.x_stride, t0_ * g.hop - L / 2, g.span, g.N,
+                       row_aligned, tid);
+        // upstream gradient tile (and y when the log is fused): rows are T floats apart in HBM, so the copies
+        // are 4-byte async ones, all in flight together; columns past the last frame are zero
+        float* gt_ = gt + slot * 2 * tile_words;
+        float* yt_ = gt_ + tile_words;
+        const long long base = (long long)b_ * g.M * g.T + t0_;
+        for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
+            const int m = idx >> tt_shift, tt = idx & (g.TT - 1);   // consecutive lanes: consecutive frames
+            const bool ok = tt < nfr_;
+            const long long off = base + (long long)m * g.T + (ok ? tt : 0);
+            cp_async4_zfill(gt_ + m * TS + tt, gy + off, ok);
+            if (do_log) cp_async4_zfill(yt_ + m * TS + tt, y + off, ok);
+        }
+    };
+    const bool ahead = g.lookahead != 0;
+    if (ahead && int(blockIdx.x) < total_tiles) issue_tile(blockIdx.x, 0);
+    int it = 0;
+    for (int tix = blockIdx.x; tix < total_tiles; tix += gridDim.x, ++it) {
         const int b = tix / g.tiles_per_clip;
         const int tile_i = tix - b * g.tiles_per_clip;
         const int t0 = tile_i * g.TT;
         const int nfr = min(g.TT, g.T - t0);
         const int p0 = t0 * g.hop - L / 2;
-        const float* xb = x + (long long)b * g.x_stride;
-        const float* xs = xs_sh + (p0 & 3);
+        const int slot = ahead ? (it & 1) : 0;
+        if (!ahead) issue_tile(tix, 0);
+        float* xs_cur = xs_sh + slot * xs_words;
+        const float* xs = xs_cur + (p0 & 3);
+        float* gtc = gt + slot * 2 * tile_words;       // this tile's dL/dmel
+        const float* ytc = gtc + tile_words;
 
-        span_issue<NT>(xs_sh, xb, p0, g.span, g.N, row_aligned, tid);
         const float mu = __ldg(means + b);
         if (NEED_DX)
             for (int i = gtid; i < g.sub_span; i += GT) priv[i] = 0.f;
-        {
-            // upstream gradient tile (and y when the log is fused): rows are T floats apart in HBM, so the
-            // copies are 4-byte async ones, all in flight together; columns past the last frame are zero
-            const long long base = (long long)b * g.M * g.T + t0;
-            for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
-                const int m = idx >> tt_shift, tt = idx & (g.TT - 1);   // consecutive lanes: consecutive frames
-                const bool ok = tt < nfr;
-                const long long off = base + (long long)m * g.T + (ok ? tt : 0);
-                cp_async4_zfill(gt + m * TS + tt, gy + off, ok);
-                if (do_log) cp_async4_zfill(yt + m * TS + tt, y + off, ok);
-            }
-        }
         cp_async_wait_all();
-        span_centre<NT>(xs_sh, p0, g.span, g.N, mu, tid);
+        span_centre<NT>(xs_cur, p0, g.span, g.N, mu, tid);
         if (do_log) {
             // dL/dmel = G / (mel + eps) = G * exp(-y); each thread touches the words it copied itself
             for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
                 const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
-                gt[m * TS + tt] *= __expf(-yt[m * TS + tt]);
+                gtc[m * TS + tt] *= __expf(-ytc[m * TS + tt]);
             }
         }
-        __syncthreads();
+        __syncthreads();   // also: every warp is done with the previous tile
+        if (ahead && tix + int(gridDim.x) < total_tiles) issue_tile(tix + gridDim.x, slot ^ 1);
 
         const int f_lo = grp * g.SF;
         const int f_hi = min(f_lo + g.SF, nfr);
@@ -597,21 +635,21 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
                 const float br = 0.5f * (z1.y + z2.y), bi = 0.5f * (z2.x - z1.x);
                 float ga, gb;
                 if (SPEC) {
-                    ga = gt[k * TS + f];
-                    gb = gt[k * TS + f + 1];
+                    ga = gtc[k * TS + f];
+                    gb = gtc[k * TS + f + 1];
                 } else {
                     // <= 2 taps per bin for a triangular bank: both issued together; longer runs loop
                     const int m0 = s_m0[k];
                     const int o0 = s_off[k], o1 = s_off[k + 1];
                     const float w0 = (o0 < o1) ? csr_w[o0] : 0.f;
                     const float w1 = (o0 + 1 < o1) ? csr_w[o0 + 1] : 0.f;
-                    const float* gp0 = gt + m0 * TS + f;
-                    const float* gp1 = gt + min(m0 + 1, g.M - 1) * TS + f;
+                    const float* gp0 = gtc + m0 * TS + f;
+                    const float* gp1 = gtc + min(m0 + 1, g.M - 1) * TS + f;
                     ga = fmaf(w1, gp1[0], w0 * gp0[0]);
                     gb = fmaf(w1, gp1[1], w0 * gp0[1]);
                     for (int o = o0 + 2; o < o1; ++o) {
                         const float w = csr_w[o];
-                        const float* gp = gt + (m0 + (o - o0)) * TS + f;
+                        const float* gp = gtc + (m0 + (o - o0)) * TS + f;
                         ga = fmaf(w, gp[0], ga);
                         gb = fmaf(w, gp[1], gb);
                     }
@@ -1178,17 +1216,18 @@ static FftInfo fft_info(int n_fft) {
 static bool has_fft_plan(int n_fft) { return fft_info(n_fft).ok; }
 
 struct LaunchPlan {
-    int path;  // 0 FFT, 1 direct DFT
+    int path;  // 0 FFT, 1 direct DFT, 2 big FFT
+    int lookahead;
     int NG, SF, TT, span, sub_span, tiles_per_clip, threads;
     int csr_ints, csr_floats;
     size_t smem;
 };
 
 static size_t smem_bytes_fft(int L, int NG, int tw_total, int span, int sub_span, int M, int TT, int csr_ints,
-                             int csr_floats, bool bwd, bool priv_dx) {
-    // backward keeps two tiles (dL/dy and, for the fused log, y)
-    const int tile_words = bwd ? 2 * round_up4(M * (TT + 1)) : M * (TT + 1);
-    return size_t(make_lay(L, NG, tw_total, span, sub_span, tile_words, csr_ints, csr_floats, priv_dx).total) * 4;
+                             int csr_floats, bool bwd, bool priv_dx, int lookahead) {
+    // backward keeps two tiles (dL/dy and, for the fused log, y); the look-ahead doubles them and the span
+    const int tile_words = bwd ? (2 + 2 * lookahead) * round_up4(M * (TT + 1)) : M * (TT + 1);
+    return size_t(make_lay(L, NG, tw_total, span, sub_span, tile_words, csr_ints, csr_floats, priv_dx, 1 + lookahead).total) * 4;
 }
 
 // Tile shape: NG groups x SF frames per CTA tile.  scripts/tune.py sweeps on B200 (profiles/) show a
@@ -1262,9 +1301,21 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
                 const int tt = NG * SF;
                 const int64_t span64 = int64_t(tt - 1) * hop + n_fft, sub64 = int64_t(SF - 1) * hop + n_fft;
                 if (span64 <= (1 << 20)) {
-                    const size_t sm = smem_bytes_fft(n_fft, NG, fi.tw_total, int(span64), int(sub64), rows, tt, csr_ints,
-                                                     csr_floats, bwd, bwd && need_dx);
+                    size_t sm = smem_bytes_fft(n_fft, NG, fi.tw_total, int(span64), int(sub64), rows, tt, csr_ints, csr_floats,
+                                               bwd, bwd && need_dx, 0);
                     if (sm <= SMEM_MAX) {
+                        // one-tile look-ahead (double buffers) only if it does not cost a resident CTA
+                        const size_t sm2 = smem_bytes_fft(n_fft, NG, fi.tw_total, int(span64), int(sub64), rows, tt, csr_ints,
+                                                          csr_floats, bwd, bwd && need_dx, 1);
+                        const int warps_cta = NG * fi.gt / 32;
+                        const int reg_cap = std::max(1, (n_fft <= 512 && NG == 4 ? 20 : 16) / warps_cta);
+                        auto ctas = [&](size_t b) { return std::min<int>(reg_cap, int(SMEM_MAX / (b + 1024))); };
+                        lp->lookahead = 0;
+                        if (!getenv("DMEL_NO_LOOKAHEAD") && sm2 <= SMEM_MAX && ctas(sm2) >= ctas(sm)) {
+                            lp->lookahead = 1;
+                            sm = sm2;
+                        }
+                        if (getenv("DMEL_FORCE_LOOKAHEAD") && sm2 <= SMEM_MAX) { lp->lookahead = 1; sm = sm2; }
                         lp->path = 0;
                         lp->NG = NG; lp->SF = SF; lp->TT = tt;
                         lp->span = int(span64); lp->sub_span = int(sub64);
@@ -1572,6 +1623,7 @@ static Geom make_geom(int64_t B, int64_t N, int64_t stride, int32_t n_fft, int32
     g.x_stride = stride;
     g.log_eps = log_eps;
     g.row_aligned = 0;
+    g.lookahead = lp.lookahead;
     return g;
 }
 

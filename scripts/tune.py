@@ -40,8 +40,9 @@ def run(wname, steps=30):
     st = int(torch.cuda.current_stream(dev).cuda_stream)
     res = []
     ngs = {128: (8, 4), 256: (8, 4), 512: (8, 4), 1024: (4, 2), 2048: (2, 1), 4096: (1,), 8192: (1,), 16384: (1,)}[geo.n_fft]
-    for ng in ngs:
-        for sf in ((0,) if geo_big(w) else (2, 4, 8, 16, 32)):
+    default_only = os.environ.get("TUNE_DEFAULT") == "1"
+    for ng in ((0,) if default_only else ngs):
+        for sf in ((0,) if (geo_big(w) or default_only) else (2, 4, 8, 16, 32)):
             if sf:
                 os.environ["DMEL_NG"], os.environ["DMEL_SF"] = str(ng), str(sf)
             def step(i, need_dx=True):
