@@ -355,8 +355,10 @@ __device__ __forceinline__ void span_centre(float* xs_sh, int p0, int span, int 
 #define DMEL_MINB_SMALL 5
 #endif
 // Everything else keeps the 128-register budget (512 threads' worth of CTAs per SM).
-__host__ __device__ constexpr int min_ctas(int L, int NG, int NT) {
-    return (L <= 512 && NG == 4) ? DMEL_MINB_SMALL : (512 / NT > 0 ? 512 / NT : 1);
+// The dx-producing backward is limited to 4 CTAs per SM by shared memory anyway and runs faster with the full
+// 128 registers (r01e 66 us vs 71 us at 96), so only the forward and the lambda-only backward take the cap.
+__host__ __device__ constexpr int min_ctas(int L, int NG, int NT, bool full_bwd = false) {
+    return (L <= 512 && NG == 4 && !full_bwd) ? DMEL_MINB_SMALL : (512 / NT > 0 ? 512 / NT : 1);
 }
 
 // integer log2 of a power of two
@@ -511,7 +513,7 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
 // backward (persistent)
 // ----------------------------------------------------------------------------
 template <int L, int NG, bool SPEC, bool NEED_DX>
-__global__ void __launch_bounds__(NG * (L / Plan<L>::E), min_ctas(L, NG, NG * (L / Plan<L>::E)))
+__global__ void __launch_bounds__(NG * (L / Plan<L>::E), min_ctas(L, NG, NG * (L / Plan<L>::E), NEED_DX))
 dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy,
                 float* __restrict__ dx, Geom g, MelDev mel, const float* __restrict__ win_g,
                 const float2* __restrict__ tw_g, const float* __restrict__ means, WsHeader* hdr,
@@ -1283,7 +1285,7 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
     // measured optima (scripts/tune.py on B200, profiles/*tune*.log): (groups, frames per group)
     int ng_pref, sf_pref;
     switch (n_fft) {
-        case 1024: ng_pref = 2; sf_pref = 8; break;
+        case 1024: ng_pref = (bwd && need_dx) ? 4 : 2; sf_pref = (bwd && need_dx) ? 4 : 8; break;
         case 2048: ng_pref = 1; sf_pref = 8; break;
         case 4096: ng_pref = 1; sf_pref = 32; break;
         default: ng_pref = 4; sf_pref = 4; break;    // one warp per transform
@@ -1308,7 +1310,7 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
                         const size_t sm2 = smem_bytes_fft(n_fft, NG, fi.tw_total, int(span64), int(sub64), rows, tt, csr_ints,
                                                           csr_floats, bwd, bwd && need_dx, 1);
                         const int warps_cta = NG * fi.gt / 32;
-                        const int reg_cap = std::max(1, (n_fft <= 512 && NG == 4 ? 20 : 16) / warps_cta);
+                        const int reg_cap = std::max(1, (n_fft <= 512 && NG == 4 && !(bwd && need_dx) ? 20 : 16) / warps_cta);
                         auto ctas = [&](size_t b) { return std::min<int>(reg_cap, int(SMEM_MAX / (b + 1024))); };
                         lp->lookahead = 0;
                         if (!getenv("DMEL_NO_LOOKAHEAD") && sm2 <= SMEM_MAX && ctas(sm2) >= ctas(sm)) {
