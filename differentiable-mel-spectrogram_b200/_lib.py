@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = (
     "dmel_nfft_supported",
     "dmel_window_length_from_lambda",
     "dmel_workspace_bytes",
+    "dmel_workspace_y_sum_offset",
     "dmel_forward_f32",
     "dmel_backward_f32",
     "dmel_query_launch",
@@ -88,6 +89,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.dmel_window_length_from_lambda.argtypes = [c.c_float]
     lib.dmel_workspace_bytes.restype = c.c_size_t
     lib.dmel_workspace_bytes.argtypes = [c.c_int64, c.c_int32]
+    lib.dmel_workspace_y_sum_offset.restype = c.c_size_t
+    lib.dmel_workspace_y_sum_offset.argtypes = []
     lib.dmel_forward_f32.restype = c.c_int
     lib.dmel_forward_f32.argtypes = [
         c.c_void_p, c.c_int64, c.c_int64, c.c_int64,          # x, batch, n_points, stride

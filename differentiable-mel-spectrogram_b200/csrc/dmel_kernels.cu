@@ -28,6 +28,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <stddef.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -50,7 +51,9 @@ struct WsHeader {
     float centre;      // window centre in n_fft coordinates: left + win_length/2
     float inv_norm;    // 1/||w|| when normalize_window, else 1
     int32_t left;      // (n_fft - win_length)/2
-    int32_t pad_[9];
+    int32_t pad0_;
+    double y_sum;      // sum of every output element of the last forward (train.py:58's running energy)
+    int32_t pad_[6];
 };
 static_assert(sizeof(WsHeader) == 64, "header is 64 bytes");
 
@@ -243,6 +246,7 @@ dmel_prep_kernel(const float* __restrict__ x, long long x_stride, int B, int N, 
         ws.hdr->centre = float(left) + c0;
         ws.hdr->inv_norm = inv_norm;
         ws.hdr->left = left;
+        ws.hdr->y_sum = 0.0;
     }
     __syncthreads();
     if (normalize) {
@@ -370,7 +374,8 @@ __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
 template <int L, int NG, bool SPEC>
 __global__ void __launch_bounds__(NG * (L / Plan<L>::E), min_ctas(L, NG, NG * (L / Plan<L>::E)))
 dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelDev mel,
-                const float* __restrict__ win_g, const float2* __restrict__ tw_g, const float* __restrict__ means) {
+                const float* __restrict__ win_g, const float2* __restrict__ tw_g, const float* __restrict__ means,
+                WsHeader* hdr) {
     constexpr int E = Plan<L>::E, GT = L / E, NT = NG * GT, TWN = TwTotal<L>::value;
     using P0 = Pass<L, 0>;
     extern __shared__ __align__(16) float smem_f[];
@@ -407,6 +412,7 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
     const int total_tiles = g.B * g.tiles_per_clip;
     const int xs_words = round_up4(g.span + 4);
     const bool ahead = g.lookahead != 0;
+    float ysum = 0.f;
     if (ahead && int(blockIdx.x) < total_tiles) {
         const int b0 = blockIdx.x / g.tiles_per_clip;
         const int p00 = (blockIdx.x - b0 * g.tiles_per_clip) * g.TT * g.hop - L / 2;
@@ -502,11 +508,15 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
                 // lg2.approx * ln2: <= 3 ulp, i.e. ~1e-6 absolute on log-mel values (budget 1e-5 + 1e-4 |y|)
                 if (do_log) val = __logf(val + g.log_eps);
                 yb[(long long)m * g.T + tt] = val;
+                ysum += val;
             }
         }
         // the next iteration's staging only writes xs; its __syncthreads orders it after this epilogue
     }
     cp_async_wait_all();
+    // fused by-product: sum of all outputs (what train.py:58 copies the whole batch to the host for)
+    const double ytot = block_sum(double(ysum), reinterpret_cast<double*>(smem_f + lay.red));
+    if (tid == 0) atomicAdd(&hdr->y_sum, ytot);
 }
 
 // ----------------------------------------------------------------------------
@@ -782,7 +792,8 @@ __device__ __forceinline__ void big_load_pair(float2 (&v)[Plan<L>::E], const flo
 template <int L, bool SPEC>
 __global__ void __launch_bounds__(L / Plan<L>::E)
 dmel_big_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelDev mel,
-                    const float* __restrict__ win_g, const float2* __restrict__ tw_g, const float* __restrict__ means) {
+                    const float* __restrict__ win_g, const float2* __restrict__ tw_g, const float* __restrict__ means,
+                    WsHeader* hdr) {
     constexpr int E = Plan<L>::E, NT = L / E;
     extern __shared__ __align__(16) float smem_f[];
     const int TS = g.TT + 1;
@@ -799,6 +810,7 @@ dmel_big_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, 
     const float* xb = x + (long long)b * g.x_stride;
     const float mu = __ldg(means + b);
     const bool do_log = g.log_eps >= 0.f;
+    float ysum = 0.f;
     for (int i = tid; i < 256; i += NT) t_hi[i] = __ldg(tw_g + i);
     __syncthreads();
 
@@ -817,7 +829,8 @@ dmel_big_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, 
                 float* yr = y + ((long long)b * g.M + k) * g.T + t0 + f;
                 if (do_log) { pa = __logf(pa + g.log_eps); pb = __logf(pb + g.log_eps); }
                 yr[0] = pa;
-                if (f + 1 < nfr) yr[1] = pb;
+                ysum += pa;
+                if (f + 1 < nfr) { yr[1] = pb; ysum += pb; }
             } else {
                 buf[k] = make_float2(pa, pb);
             }
@@ -854,9 +867,12 @@ dmel_big_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, 
                 float val = tile[m * TS + tt];
                 if (do_log) val = __logf(val + g.log_eps);
                 yb[(long long)m * g.T + tt] = val;
+                ysum += val;
             }
         }
     }
+    const double ytot = block_sum(double(ysum), reinterpret_cast<double*>(smem_f + lay.red));
+    if (tid == 0) atomicAdd(&hdr->y_sum, ytot);
 }
 
 template <int L, bool SPEC, bool NEED_DX>
@@ -1100,6 +1116,7 @@ dmel_dft_kernel(const float* __restrict__ x, const float* __restrict__ y_in, con
     __syncthreads();
     const bool do_log = g.log_eps >= 0.f;
     if (!BWD) {
+        float ysum_dft = 0.f;
         float* yb = y_out + (long long)b * g.M * g.T + t;
         for (int m = tid; m < g.M; m += DFT_THREADS) {
             float s;
@@ -1113,7 +1130,10 @@ dmel_dft_kernel(const float* __restrict__ x, const float* __restrict__ y_in, con
             }
             if (do_log) s = logf(s + g.log_eps);
             yb[(long long)m * g.T] = s;
+            ysum_dft += s;
         }
+        const double ytot = block_sum(double(ysum_dft), red);
+        if (tid == 0) atomicAdd(&hdr->y_sum, ytot);
         return;
     }
     // backward: GP[k], Z[k] = c_k * 2 GP X  (c_k = 1/2 off the DC/Nyquist bins, whose X is real)
@@ -1415,7 +1435,7 @@ static int launch_fwd_t(const float* x, float* y, const Geom& g, const MelDev& m
     if ((rc = set_smem(dmel_fwd_kernel<L, NG, SPEC>, lp.smem))) return rc;
     const unsigned grid = persistent_grid(dmel_fwd_kernel<L, NG, SPEC>, lp, int64_t(g.B) * g.tiles_per_clip);
     ProfScope prof(PROF_FWD, st);
-    dmel_fwd_kernel<L, NG, SPEC><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means);
+    dmel_fwd_kernel<L, NG, SPEC><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means, ws.hdr);
     return check_launch("dmel_fwd_kernel");
 }
 
@@ -1456,10 +1476,10 @@ static int launch_big_fwd(const float* x, float* y, const Geom& g, const MelDev&
     ProfScope prof(PROF_FWD, st);
     if (spec) {
         if ((rc = set_smem(dmel_big_fwd_kernel<L, true>, lp.smem))) return rc;
-        dmel_big_fwd_kernel<L, true><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means);
+        dmel_big_fwd_kernel<L, true><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means, ws.hdr);
     } else {
         if ((rc = set_smem(dmel_big_fwd_kernel<L, false>, lp.smem))) return rc;
-        dmel_big_fwd_kernel<L, false><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means);
+        dmel_big_fwd_kernel<L, false><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means, ws.hdr);
     }
     return check_launch("dmel_big_fwd_kernel");
 }
@@ -1770,3 +1790,5 @@ extern "C" DMEL_API int dmel_profile_read(int32_t kind, double* total_ms, long l
     *launches = (long long)(v.size() / 2);
     return DMEL_OK;
 }
+
+extern "C" DMEL_API size_t dmel_workspace_y_sum_offset(void) { return offsetof(WsHeader, y_sum); }

@@ -64,6 +64,8 @@ class MelSpectrogramLayer(nn.Module):
         self.n_time = n_points // hop_length + 1
         self.log_eps = log_eps
         self._mirror = _LambdaMirror()
+        # 0-d fp64 device tensor: sum of the last forward's output, produced inside the kernel (train.py:58)
+        self.last_energy = None
 
     def forward(self, x):
         dev = _resolve_device(self.device, self.lambd)
@@ -78,10 +80,11 @@ class MelSpectrogramLayer(nn.Module):
             # the reference fails on the slice assignment models.py:54
             raise RuntimeError(f"input has {n_points} points -> {n_points // self.hop_length + 1} frames, "
                                f"layer was built for n_time={self.n_time}")
-        return dmel(x, self.lambd, hop_length=self.hop_length, optimized=self.optimized,
-                    normalize_window=self.normalize_window, n_mels=self.n_mels, sample_rate=self.sample_rate,
-                    f_min=self.f_min, f_max=self.f_max, log_eps=self.log_eps,
-                    lambd_value=self._mirror.get(self.lambd))
+        y, self.last_energy = dmel(x, self.lambd, hop_length=self.hop_length, optimized=self.optimized,
+                                   normalize_window=self.normalize_window, n_mels=self.n_mels,
+                                   sample_rate=self.sample_rate, f_min=self.f_min, f_max=self.f_max,
+                                   log_eps=self.log_eps, lambd_value=self._mirror.get(self.lambd), return_energy=True)
+        return y
 
     def extra_repr(self):
         return (f"n_mels={self.n_mels}, sample_rate={self.sample_rate}, hop_length={self.hop_length}, "
@@ -100,6 +103,7 @@ class SpectrogramLayer(nn.Module):
         self.normalize_window = normalize_window
         self.log_eps = log_eps
         self._mirror = _LambdaMirror()
+        self.last_energy = None
 
     def forward(self, x):
         dev = _resolve_device(self.device, self.lambd)
@@ -109,9 +113,9 @@ class SpectrogramLayer(nn.Module):
                 "fallback; move the module with .to('cuda')")
         if x.device != dev:
             x = x.to(dev, non_blocking=True)
-        s = dmel(x, self.lambd, hop_length=self.hop_length, optimized=self.optimized,
-                 normalize_window=self.normalize_window, n_mels=0, log_eps=self.log_eps,
-                 lambd_value=self._mirror.get(self.lambd))
+        s, self.last_energy = dmel(x, self.lambd, hop_length=self.hop_length, optimized=self.optimized,
+                                   normalize_window=self.normalize_window, n_mels=0, log_eps=self.log_eps,
+                                   lambd_value=self._mirror.get(self.lambd), return_energy=True)
         if self.optimized and tuple(s.shape[2:]) != tuple(self.size):
             # models.py:186,198: the reference allocates `size` and assigns the (F, T) spectrogram into it
             raise RuntimeError(f"spectrogram of shape {tuple(s.shape[2:])} does not fit size={tuple(self.size)}")

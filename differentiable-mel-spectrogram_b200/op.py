@@ -122,11 +122,15 @@ class DmelFunction(torch.autograd.Function):
             ctx.save_for_backward(x, y)
         else:
             ctx.save_for_backward(x)
-        return y
+        # fused by-product: sum of all outputs, one fp64 living in the workspace header (no extra launch)
+        off = lib.dmel_workspace_y_sum_offset()
+        energy = ws[off:off + 8].view(torch.float64)[0]
+        ctx.mark_non_differentiable(energy)
+        return y, energy
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, grad_y: torch.Tensor):
+    def backward(ctx, grad_y: torch.Tensor, _grad_energy=None):
         lib = _lib.load()
         geo = ctx.geo
         saved = ctx.saved_tensors
@@ -156,7 +160,7 @@ class DmelFunction(torch.autograd.Function):
 def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bool,
          normalize_window: bool = False, n_mels: int = 0, sample_rate: int = 0, f_min: float = 0.0,
          f_max: Optional[float] = None, log_eps: Optional[float] = None, remove_mean: bool = True,
-         lambd_value: Optional[float] = None) -> torch.Tensor:
+         lambd_value: Optional[float] = None, return_energy: bool = False):
     """Functional form of both layers.
 
     x: (B, N) CUDA tensor (fp32; fp64/fp16 inputs are cast to fp32 — the reference's fp64
@@ -164,7 +168,9 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
     (B, 1, rows, N//hop + 1) fp32, contiguous: the linear (mel) power spectrogram, or its
     log(. + log_eps) when log_eps is given (the classifiers' energy_normalize, models.py:72).
     n_mels == 0 selects spectrogram mode (models.py:171-200).  `lambd_value`, if given, must equal
-    lambd's current value (it only saves the device->host read that picks n_fft).
+    lambd's current value (it only saves the device->host read that picks n_fft).  With `return_energy`
+    the result is `(y, energy)`, energy a 0-d fp64 device tensor = y.sum() computed inside the forward kernel
+    (what train.py:58 copies the whole spectrogram batch to the host for).
     """
     if x.dim() != 2:
         raise ValueError(f"expected x of shape (batch, n_points), got {tuple(x.shape)}")
@@ -193,7 +199,8 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
     eps = -1.0 if log_eps is None else float(log_eps)
     if log_eps is not None and log_eps < 0:
         raise ValueError("log_eps must be >= 0")
-    return DmelFunction.apply(x, lambd, geo, bank, eps, flags, lam_value)
+    y, energy = DmelFunction.apply(x, lambd, geo, bank, eps, flags, lam_value)
+    return (y, energy) if return_energy else y
 
 
 def query_launch(batch: int, n_points: int, n_fft: int, hop: int, rows: int, bank_nnz: int = 0,

@@ -90,6 +90,11 @@ DMEL_API int32_t dmel_window_length_from_lambda(float lambda);
  * means, per-clip dx sums, fp64 dL/dlambda accumulator).                            */
 DMEL_API size_t dmel_workspace_bytes(int64_t batch, int32_t n_fft);
 
+/* Byte offset inside the workspace of one fp64 that dmel_forward_f32 leaves behind: the sum of all
+ * elements of y (log-mel when the log is fused).  train.py:58 copies every spectrogram batch to the
+ * host just to add it up (`running_energy`); reading these 8 bytes replaces that copy.            */
+DMEL_API size_t dmel_workspace_y_sum_offset(void);
+
 /* Forward:  y[b,0,m,t] of models.py:33-56 (n_mels > 0) or models.py:182-200
  * (n_mels == 0: "spectrogram mode", rows are the n_fft/2+1 frequency bins).
  *   x           [batch, n_points] fp32, row stride x_row_stride elements
