@@ -95,6 +95,10 @@ class _on_device:
         return False
 
 
+_ws_bytes_cache: dict = {}
+_Y_SUM_OFFSET = [-1]
+
+
 class DmelFunction(torch.autograd.Function):
     """y = DMEL(x, lambd); saves only x, lambd (and y when the log is fused) plus the small
     workspace (per-clip means, window, twiddles) — spectra are recomputed in backward."""
@@ -105,7 +109,10 @@ class DmelFunction(torch.autograd.Function):
         lib = _lib.load()
         dev = x.device
         y = torch.empty((geo.batch, 1, geo.rows, geo.n_frames), dtype=torch.float32, device=dev)
-        ws_bytes = lib.dmel_workspace_bytes(geo.batch, geo.n_fft)
+        wkey = (geo.batch, geo.n_fft)
+        ws_bytes = _ws_bytes_cache.get(wkey)
+        if ws_bytes is None:
+            ws_bytes = _ws_bytes_cache[wkey] = lib.dmel_workspace_bytes(geo.batch, geo.n_fft)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with _on_device(dev):
             rc = lib.dmel_forward_f32(
@@ -123,7 +130,9 @@ class DmelFunction(torch.autograd.Function):
         else:
             ctx.save_for_backward(x)
         # fused by-product: sum of all outputs, one fp64 living in the workspace header (no extra launch)
-        off = lib.dmel_workspace_y_sum_offset()
+        off = _Y_SUM_OFFSET[0]
+        if off < 0:
+            off = _Y_SUM_OFFSET[0] = lib.dmel_workspace_y_sum_offset()
         energy = ws[off:off + 8].view(torch.float64)[0]
         ctx.mark_non_differentiable(energy)
         return y, energy
@@ -187,20 +196,33 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
     # host mirror of lambd (the layers do, keyed on the parameter's version counter) pass it in
     lam_value = float(lambd.detach().to(torch.float32).item()) if lambd_value is None else float(lambd_value)
     B, N = x.shape
-    geo = resolve_geometry(B, N, hop_length, lam_value, optimized, n_mels)
-    lib = _lib.load()
-    if not lib.dmel_nfft_supported(geo.n_fft):
-        raise _lib.DmelError(f"n_fft={geo.n_fft} (lambd={lam_value}) has no kernel")
-    bank = None
-    if n_mels > 0:
-        fmax = f_max if f_max is not None else sample_rate // 2
-        bank = device_bank(geo.n_freqs, f_min, fmax, n_mels, sample_rate, x.device)
-    flags = (_lib.FLAG_NORMALIZE_WINDOW if normalize_window else 0) | (0 if remove_mean else _lib.FLAG_KEEP_MEAN)
-    eps = -1.0 if log_eps is None else float(log_eps)
     if log_eps is not None and log_eps < 0:
         raise ValueError("log_eps must be >= 0")
+    # everything below depends only on these scalars: resolve once, reuse while they repeat (training loops)
+    key = (B, N, hop_length, lam_value, optimized, normalize_window, n_mels, sample_rate, f_min, f_max, log_eps, remove_mean,
+           x.device.index)
+    plan = _plan_cache.get(key)
+    if plan is None:
+        geo = resolve_geometry(B, N, hop_length, lam_value, optimized, n_mels)
+        lib = _lib.load()
+        if not lib.dmel_nfft_supported(geo.n_fft):
+            raise _lib.DmelError(f"n_fft={geo.n_fft} (lambd={lam_value}) has no kernel")
+        bank = None
+        if n_mels > 0:
+            fmax = f_max if f_max is not None else sample_rate // 2
+            bank = device_bank(geo.n_freqs, f_min, fmax, n_mels, sample_rate, x.device)
+        flags = (_lib.FLAG_NORMALIZE_WINDOW if normalize_window else 0) | (0 if remove_mean else _lib.FLAG_KEEP_MEAN)
+        eps = -1.0 if log_eps is None else float(log_eps)
+        plan = (geo, bank, eps, flags)
+        if len(_plan_cache) > 64:
+            _plan_cache.clear()
+        _plan_cache[key] = plan
+    geo, bank, eps, flags = plan
     y, energy = DmelFunction.apply(x, lambd, geo, bank, eps, flags, lam_value)
     return (y, energy) if return_energy else y
+
+
+_plan_cache: dict = {}
 
 
 def query_launch(batch: int, n_points: int, n_fft: int, hop: int, rows: int, bank_nnz: int = 0,
