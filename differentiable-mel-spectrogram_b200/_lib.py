@@ -61,7 +61,7 @@ _lib = None
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ for sm_100a into libdmel_b200.so (in-tree) with nvcc."""
-    srcs = [os.path.join(CSRC_DIR, f) for f in ("dmel_kernels.cu", "fft_device.cuh")]
+    srcs = [os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith((".cu", ".cuh")) or f == "Makefile"]
     srcs.append(os.path.join(_HERE, "..", "include", "dmel.h"))
     if not force and os.path.exists(LIB_PATH):
         newest = max(os.path.getmtime(s) for s in srcs if os.path.exists(s))

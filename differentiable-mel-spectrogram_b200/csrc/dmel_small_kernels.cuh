@@ -1,0 +1,181 @@
+// dmel_small_kernels.cuh — prep (means, window, twiddles), zero-init and finalize kernels
+// Part of libdmel_b200.so (single translation unit, see dmel_kernels.cu for the overview).
+#pragma once
+#include "dmel_common.cuh"
+
+namespace dmel {
+
+// ----------------------------------------------------------------------------
+// prep: means + window + twiddles
+// ----------------------------------------------------------------------------
+constexpr int PREP_THREADS = 256;
+
+// host mirror of fft_device.cuh's Plan<L> (np == 0: no FFT plan, direct-DFT path)
+struct PlanDesc {
+    int np;
+    int r[4];
+};
+
+__global__ void __launch_bounds__(PREP_THREADS)
+dmel_prep_kernel(const float* __restrict__ x, long long x_stride, int B, int N, float lam_abs, int win_length,
+                 int n_fft, int flags, WsView ws, PlanDesc plan) {
+    __shared__ double red[32];
+    const int tid = threadIdx.x;
+    const int normalize = flags & DMEL_FLAG_NORMALIZE_WINDOW;
+    if (int(blockIdx.x) < B) {
+        if (flags & DMEL_FLAG_KEEP_MEAN) {
+            if (tid == 0) ws.means[blockIdx.x] = 0.f;
+            return;
+        }
+        // models.py:38  x[idx] - torch.mean(x[idx])
+        const float* xb = x + (long long)blockIdx.x * x_stride;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int i0 = 0;
+        if ((reinterpret_cast<uintptr_t>(xb) & 15) == 0) {
+            // 16-byte loads, 8 independent ones in flight per thread
+            const float4* x4 = reinterpret_cast<const float4*>(xb);
+            const int n4 = N >> 2;
+            int q = tid;
+            for (; q + 7 * PREP_THREADS < n4; q += 8 * PREP_THREADS) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(x4 + q + u * PREP_THREADS);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+            }
+            for (; q < n4; q += PREP_THREADS) {
+                const float4 v = __ldg(x4 + q);
+                acc[0] += (v.x + v.y) + (v.z + v.w);
+            }
+            i0 = n4 << 2;
+        }
+        for (int i = i0 + tid; i < N; i += PREP_THREADS) acc[1] += __ldg(xb + i);
+        double part = 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) part += double(acc[u]);
+        double tot = block_sum(part, red);
+        if (tid == 0) ws.means[blockIdx.x] = float(tot / double(N));
+        return;
+    }
+    // time_frequency.py:21-30; torch.stft centre-pads the window to n_fft
+    const int left = (n_fft - win_length) / 2;
+    const float lam = lam_abs + 1e-15f;
+    const float c0 = 0.5f * float(win_length);
+    const float inv_lam3 = 1.0f / (lam * lam * lam);
+    double s2 = 0.0, sq = 0.0;
+    for (int n = tid; n < n_fft; n += PREP_THREADS) {
+        const int m = n - left;
+        float w = 0.f;
+        if (m >= 0 && m < win_length) {
+            const float d = float(m) - c0;
+            const float t = d / lam;
+            w = expf(-0.5f * (t * t));
+            s2 += double(w) * double(w);
+            sq += double(w) * double(w) * double(d * d * inv_lam3);
+        }
+        ws.win[n] = w;
+        if (plan.np < 0 && n < 256) {  // big-FFT path: t_hi[h] = exp(-2*pi*i*128h/n_fft), t_lo[l] = exp(-2*pi*i*l/n_fft)
+            double sn, cs;
+            const double idx = n < 128 ? 128.0 * double(n) : double(n - 128);
+            sincospi(-2.0 * idx / double(n_fft), &sn, &cs);
+            ws.tw[n] = make_float2(float(cs), float(sn));
+        }
+        if (plan.np == 0) {  // direct-DFT path: plain table exp(-2*pi*i*n/n_fft)
+            double sn, cs;
+            sincospi(-2.0 * double(n) / double(n_fft), &sn, &cs);
+            ws.tw[n] = make_float2(float(cs), float(sn));
+        }
+    }
+    // FFT path: per-pass tables T_p[r-1][k] = exp(-2*pi*i*k*r/(NS_p*R_p)) (fft_device.cuh, TwOffset)
+    {
+        int off = 0, ns = plan.r[0];
+        for (int p = 1; p < plan.np; ++p) {
+            const int R = plan.r[p], cnt = (R - 1) * ns;
+            for (int e = tid; e < cnt; e += PREP_THREADS) {
+                const int r = e / ns + 1, k = e - (r - 1) * ns;
+                double sn, cs;
+                sincospi(-2.0 * double(k) * double(r) / (double(ns) * double(R)), &sn, &cs);
+                ws.tw[off + e] = make_float2(float(cs), float(sn));
+            }
+            off += cnt;
+            ns *= R;
+        }
+    }
+    const double S2 = block_sum(s2, red);
+    __shared__ float sh_scale;
+    __syncthreads();
+    const double SQ = block_sum(sq, red);
+    if (tid == 0) {
+        // S2 is valid in thread 0 only (block_sum contract)
+        float inv_norm = 1.f, cprime = 0.f;
+        if (normalize) {
+            inv_norm = 1.0f / sqrtf(float(S2));
+            cprime = float(SQ / S2);
+        }
+        sh_scale = inv_norm;
+        ws.hdr->inv_lam3 = inv_lam3;
+        ws.hdr->cprime = cprime;
+        ws.hdr->centre = float(left) + c0;
+        ws.hdr->inv_norm = inv_norm;
+        ws.hdr->left = left;
+        ws.hdr->y_sum = 0.0;
+    }
+    __syncthreads();
+    if (normalize) {
+        const float sc = sh_scale;
+        for (int n = tid; n < n_fft; n += PREP_THREADS) ws.win[n] *= sc;
+    }
+}
+
+// ----------------------------------------------------------------------------
+// finalize: dx -= mean(dx) per clip; dL/dlambda -> fp32 with sign(lambda)
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dmel_finalize_kernel(float* __restrict__ dx, int B, int N, int chunks_per_clip, const double* __restrict__ clipsum,
+                     const WsHeader* hdr, float sign, float* __restrict__ grad_lambda) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *grad_lambda = float(double(sign) * hdr->dlam_acc);
+    if (dx == nullptr) return;
+    const int b = blockIdx.x / chunks_per_clip;
+    const int c = blockIdx.x - b * chunks_per_clip;
+    if (b >= B) return;
+    if (clipsum == nullptr) return;  // DMEL_FLAG_KEEP_MEAN: no mean-removal adjoint
+    const float mu = float(clipsum[b] / double(N));
+    float* dxb = dx + (long long)b * N;
+    const int per = (((N + chunks_per_clip - 1) / chunks_per_clip) + 3) & ~3;
+    const int lo = c * per, hi = min(N, lo + per);
+    if ((reinterpret_cast<uintptr_t>(dxb) & 15) == 0) {
+        float4* d4 = reinterpret_cast<float4*>(dxb);
+        const int q_hi = hi >> 2;
+        for (int q = (lo >> 2) + threadIdx.x; q < q_hi; q += 256) {
+            float4 v = d4[q];
+            v.x -= mu; v.y -= mu; v.z -= mu; v.w -= mu;
+            d4[q] = v;
+        }
+        for (int i = (q_hi << 2) + threadIdx.x; i < hi; i += 256) dxb[i] -= mu;
+    } else {
+        for (int i = lo + threadIdx.x; i < hi; i += 256) dxb[i] -= mu;
+    }
+}
+
+// one launch instead of three memsets: dx (halos are reduced into it), per-clip sums, dL/dlambda accumulator
+__global__ void __launch_bounds__(256)
+dmel_zero_kernel(float* __restrict__ dx, long long n_dx, double* __restrict__ clipsum, int B, WsHeader* hdr) {
+    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * 256;
+    if (gid == 0) hdr->dlam_acc = 0.0;
+    if (clipsum)
+        for (long long i = gid; i < B; i += nthreads) clipsum[i] = 0.0;
+    if (dx) {
+        if ((reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
+            float4* d4 = reinterpret_cast<float4*>(dx);
+            const long long n4 = n_dx >> 2;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (long long i = gid; i < n4; i += nthreads) d4[i] = z;
+            for (long long i = (n4 << 2) + gid; i < n_dx; i += nthreads) dx[i] = 0.f;
+        } else {
+            for (long long i = gid; i < n_dx; i += nthreads) dx[i] = 0.f;
+        }
+    }
+}
+
+}  // namespace dmel
