@@ -359,23 +359,41 @@ def main():
         kern[name] = (tot.value / max(cnt.value, 1), cnt.value)
     lib.dmel_profile_enable(0)
 
-    # training mode of the reference (x is data, only lambd trains): backward without dL/dx
-    def lambda_only_step(i):
+    # training mode of the reference (x is data, only lambd trains): forward-mode kernel (y and dy/dlambda in one
+    # pass) + dot-product backward; and, for comparison, the recomputing backward without dL/dx
+    dys = [torch.empty(B, 1, M, T, device=dev) for _ in range(min(R, 2))]
+
+    def lambda_only_step(i, jvp):
         s = i % R
         st = int(torch.cuda.current_stream(dev).cuda_stream)
-        lib.dmel_forward_f32(xs[s].data_ptr(), B, N, N, lam, geo.win_length, geo.n_fft, hop, M, bank.ref(), LOG_EPS, 0,
-                             ys[s].data_ptr(), wss[s].data_ptr(), ws_bytes, st)
-        lib.dmel_backward_f32(xs[s].data_ptr(), B, N, N, lam, geo.win_length, geo.n_fft, hop, M, bank.ref(), LOG_EPS, 0,
-                              ys[s].data_ptr(), Gs[s].data_ptr(), None, dls[s].data_ptr(), wss[s].data_ptr(), ws_bytes, 1, st)
-    for i in range(3):
-        lambda_only_step(i)
-    torch.cuda.synchronize(dev)
-    ev0.record()
-    for i in range(kprof_steps):
-        lambda_only_step(i)
-    ev1.record()
-    torch.cuda.synchronize(dev)
-    ms_lambda_only = ev0.elapsed_time(ev1) / kprof_steps
+        if jvp:
+            d = dys[i % len(dys)]
+            rc = lib.dmel_forward_jvp_f32(xs[s].data_ptr(), B, N, N, lam, geo.win_length, geo.n_fft, hop, M, bank.ref(), LOG_EPS, 0,
+                                          ys[s].data_ptr(), d.data_ptr(), wss[s].data_ptr(), ws_bytes, st)
+            assert rc == 0, lib.dmel_status_string(rc)
+            rc = lib.dmel_lambda_grad_f32(Gs[s].data_ptr(), d.data_ptr(), B * M * T, lam, dls[s].data_ptr(), wss[s].data_ptr(),
+                                          ws_bytes, st)
+        else:
+            lib.dmel_forward_f32(xs[s].data_ptr(), B, N, N, lam, geo.win_length, geo.n_fft, hop, M, bank.ref(), LOG_EPS, 0,
+                                 ys[s].data_ptr(), wss[s].data_ptr(), ws_bytes, st)
+            rc = lib.dmel_backward_f32(xs[s].data_ptr(), B, N, N, lam, geo.win_length, geo.n_fft, hop, M, bank.ref(), LOG_EPS, 0,
+                                       ys[s].data_ptr(), Gs[s].data_ptr(), None, dls[s].data_ptr(), wss[s].data_ptr(), ws_bytes, 1, st)
+        assert rc == 0, lib.dmel_status_string(rc)
+
+    ms_lambda = {}
+    for tag, jvp in (("jvp", True), ("recompute", False)):
+        if jvp and not lib.dmel_jvp_supported(geo.n_fft):
+            continue
+        for i in range(3):
+            lambda_only_step(i, jvp)
+        torch.cuda.synchronize(dev)
+        ev0.record()
+        for i in range(kprof_steps):
+            lambda_only_step(i, jvp)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        ms_lambda[tag] = ev0.elapsed_time(ev1) / kprof_steps
+    ms_lambda_only = ms_lambda.get("jvp", ms_lambda["recompute"])
 
     # ---- e2e through the public module from pinned host memory ----
     e2e = None
@@ -495,8 +513,10 @@ def main():
             "gpu_launches": gpu_launches,
             "kernels_ms": {k: round(v[0], 6) for k, v in kern.items()},
             "lambda_only": {"ms_per_step": ms_lambda_only, "value": audio_s / (ms_lambda_only * 1e-3), "unit": UNIT,
-                            "note": "per GPU, eager launches: forward + backward with dL/dlambda only (x without grad, the "
-                                    "reference's training case, models.py:19 / main.py:27)"},
+                            "ms_per_step_by_method": {k: round(v, 6) for k, v in ms_lambda.items()},
+                            "note": "per GPU, eager launches: the reference's training case (x without grad, only lambd "
+                                    "trains, models.py:19 / main.py:27): forward-mode kernel + dot-product backward (jvp) "
+                                    "vs forward + recomputing backward without dL/dx (recompute)"},
             "roofline": {"bound": "hbm", "kernel": f"dmel_{dom}_kernel<{w['n_fft']}>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algorithmic_bytes(w, dom),

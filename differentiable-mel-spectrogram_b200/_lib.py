@@ -26,6 +26,9 @@ EXPORTED_SYMBOLS = (
     "dmel_workspace_bytes",
     "dmel_workspace_y_sum_offset",
     "dmel_forward_f32",
+    "dmel_forward_jvp_f32",
+    "dmel_jvp_supported",
+    "dmel_lambda_grad_f32",
     "dmel_backward_f32",
     "dmel_query_launch",
     "dmel_launch_count",
@@ -99,6 +102,13 @@ def _declare(lib: ctypes.CDLL) -> None:
         c.c_int32, c.c_void_p,                                # flags, y
         c.c_void_p, c.c_size_t, c.c_void_p,                   # workspace, bytes, stream
     ]
+    lib.dmel_forward_jvp_f32.restype = c.c_int
+    lib.dmel_forward_jvp_f32.argtypes = lib.dmel_forward_f32.argtypes[:13] + [c.c_void_p] + lib.dmel_forward_f32.argtypes[13:]
+    lib.dmel_jvp_supported.restype = c.c_int
+    lib.dmel_jvp_supported.argtypes = [c.c_int32]
+    lib.dmel_lambda_grad_f32.restype = c.c_int
+    lib.dmel_lambda_grad_f32.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_float, c.c_void_p, c.c_void_p, c.c_size_t,
+                                         c.c_void_p]
     lib.dmel_backward_f32.restype = c.c_int
     lib.dmel_backward_f32.argtypes = [
         c.c_void_p, c.c_int64, c.c_int64, c.c_int64,

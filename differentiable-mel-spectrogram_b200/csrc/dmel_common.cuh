@@ -21,7 +21,9 @@ struct WsHeader {
     int32_t left;      // (n_fft - win_length)/2
     int32_t pad0_;
     double y_sum;      // sum of every output element of the last forward (train.py:58's running energy)
-    int32_t pad_[6];
+    double jvp_acc;    // sum(dL/dy * dy/d|lambda|) of dmel_lambda_grad_kernel (self-resetting)
+    uint32_t jvp_ticket;
+    int32_t pad_[3];
 };
 static_assert(sizeof(WsHeader) == 64, "header is 64 bytes");
 

@@ -107,9 +107,11 @@ struct LaunchPlan {
 };
 
 static size_t smem_bytes_fft(int L, int NG, int tw_total, int span, int sub_span, int M, int TT, int csr_ints,
-                             int csr_floats, bool bwd, bool priv_dx, int lookahead) {
-    // backward keeps two tiles (dL/dy and, for the fused log, y); the look-ahead doubles them and the span
-    const int tile_words = bwd ? (2 + 2 * lookahead) * round_up4(M * (TT + 1)) : M * (TT + 1);
+                             int csr_floats, bool bwd, bool priv_dx, int lookahead, bool jvp = false) {
+    // backward keeps two tiles (dL/dy and, for the fused log, y); the look-ahead doubles them and the span.
+    // the JVP forward keeps two planes (mel, dmel/dlambda)
+    const int tile_words = bwd ? (2 + 2 * lookahead) * round_up4(M * (TT + 1))
+                               : (jvp ? 2 * round_up4(M * (TT + 1)) : M * (TT + 1));
     return size_t(make_lay(L, NG, tw_total, span, sub_span, tile_words, csr_ints, csr_floats, priv_dx, 1 + lookahead).total) * 4;
 }
 
@@ -120,7 +122,7 @@ static size_t smem_bytes_fft(int L, int NG, int tw_total, int span, int sub_span
 // until the tile fits shared memory or the clip.
 // DMEL_NG / DMEL_SF in the environment pin the choice (tuning experiments).
 static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int csr_ints, int csr_floats, bool bwd,
-                       bool need_dx, LaunchPlan* lp) {
+                       bool need_dx, LaunchPlan* lp, bool jvp = false) {
     (void)B;
     const int64_t T64 = N / hop + 1;
     if (T64 > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
@@ -185,11 +187,11 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
                 const int64_t span64 = int64_t(tt - 1) * hop + n_fft, sub64 = int64_t(SF - 1) * hop + n_fft;
                 if (span64 <= (1 << 20)) {
                     size_t sm = smem_bytes_fft(n_fft, NG, fi.tw_total, int(span64), int(sub64), rows, tt, csr_ints, csr_floats,
-                                               bwd, bwd && need_dx, 0);
+                                               bwd, bwd && need_dx, 0, jvp);
                     if (sm <= SMEM_MAX) {
                         // one-tile look-ahead (double buffers) only if it does not cost a resident CTA
                         const size_t sm2 = smem_bytes_fft(n_fft, NG, fi.tw_total, int(span64), int(sub64), rows, tt, csr_ints,
-                                                          csr_floats, bwd, bwd && need_dx, 1);
+                                                          csr_floats, bwd, bwd && need_dx, 1, jvp);
                         const int warps_cta = NG * fi.gt / 32;
                         const int reg_cap = std::max(1, (n_fft <= 512 && NG == 4 && !(bwd && need_dx) ? 20 : 16) / warps_cta);
                         auto ctas = [&](size_t b) { return std::min<int>(reg_cap, int(SMEM_MAX / (b + 1024))); };
@@ -289,14 +291,14 @@ static unsigned persistent_grid(K kernel, const LaunchPlan& lp, int64_t total_ti
     return unsigned(std::min<int64_t>(total_tiles, cap));
 }
 
-template <int L, int NG, bool SPEC>
-static int launch_fwd_t(const float* x, float* y, const Geom& g, const MelDev& mel, const WsView& ws,
+template <int L, int NG, bool SPEC, bool JVP>
+static int launch_fwd_t(const float* x, float* y, float* dy, const Geom& g, const MelDev& mel, const WsView& ws,
                         const LaunchPlan& lp, cudaStream_t st) {
     int rc;
-    if ((rc = set_smem(dmel_fwd_kernel<L, NG, SPEC>, lp.smem))) return rc;
-    const unsigned grid = persistent_grid(dmel_fwd_kernel<L, NG, SPEC>, lp, int64_t(g.B) * g.tiles_per_clip);
+    if ((rc = set_smem(dmel_fwd_kernel<L, NG, SPEC, JVP>, lp.smem))) return rc;
+    const unsigned grid = persistent_grid(dmel_fwd_kernel<L, NG, SPEC, JVP>, lp, int64_t(g.B) * g.tiles_per_clip);
     ProfScope prof(PROF_FWD, st);
-    dmel_fwd_kernel<L, NG, SPEC><<<grid, lp.threads, lp.smem, st>>>(x, y, g, mel, ws.win, ws.tw, ws.means, ws.hdr);
+    dmel_fwd_kernel<L, NG, SPEC, JVP><<<grid, lp.threads, lp.smem, st>>>(x, y, dy, g, mel, ws.win, ws.tw, ws.means, ws.hdr);
     return check_launch("dmel_fwd_kernel");
 }
 
@@ -313,9 +315,14 @@ static int launch_bwd_t(const float* x, const float* y, const float* gy, float* 
 }
 
 template <int L, int NG>
-static int launch_fwd(const float* x, float* y, const Geom& g, const MelDev& mel, bool spec, const WsView& ws,
+static int launch_fwd(const float* x, float* y, float* dy, const Geom& g, const MelDev& mel, bool spec, const WsView& ws,
                       const LaunchPlan& lp, cudaStream_t st) {
-    return spec ? launch_fwd_t<L, NG, true>(x, y, g, mel, ws, lp, st) : launch_fwd_t<L, NG, false>(x, y, g, mel, ws, lp, st);
+    if (dy) {
+        return spec ? launch_fwd_t<L, NG, true, true>(x, y, dy, g, mel, ws, lp, st)
+                    : launch_fwd_t<L, NG, false, true>(x, y, dy, g, mel, ws, lp, st);
+    }
+    return spec ? launch_fwd_t<L, NG, true, false>(x, y, nullptr, g, mel, ws, lp, st)
+                : launch_fwd_t<L, NG, false, false>(x, y, nullptr, g, mel, ws, lp, st);
 }
 
 template <int L, int NG>
@@ -510,10 +517,10 @@ static Geom make_geom(int64_t B, int64_t N, int64_t stride, int32_t n_fft, int32
     return g;
 }
 
-extern "C" DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
-                                int32_t win_length, int32_t n_fft, int32_t hop, int32_t n_mels,
-                                const dmel_melbank* bank, float log_eps, int32_t flags, float* y,
-                                void* workspace, size_t workspace_bytes, void* cuda_stream) {
+static int forward_impl(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
+                        int32_t win_length, int32_t n_fft, int32_t hop, int32_t n_mels, const dmel_melbank* bank,
+                        float log_eps, int32_t flags, float* y, float* dy, void* workspace, size_t workspace_bytes,
+                        void* cuda_stream) {
     if (!y) return DMEL_ERR_NULL_POINTER;
     int rc = validate(x, batch, n_points, x_row_stride, win_length, n_fft, hop, n_mels, bank, workspace, workspace_bytes);
     if (rc) return rc;
@@ -522,8 +529,9 @@ extern "C" DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t 
     const int rows = spec ? n_fft / 2 + 1 : n_mels;
     LaunchPlan lp{};
     if ((rc = plan_launch(batch, n_points, n_fft, hop, rows, spec ? 0 : round_up4(n_mels) + round_up4(n_mels + 1), spec ? 0 : bank->mel_nnz, false,
-                          false, &lp)))
+                          false, &lp, dy != nullptr)))
         return rc;
+    if (dy && lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;   // the JVP forward exists for the tiled FFT path only
     if (int64_t(batch) * lp.tiles_per_clip > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
     WsView ws = ws_view(workspace, batch, n_fft);
     if ((rc = run_prep(x, batch, n_points, x_row_stride, fabsf(lambda), win_length, n_fft, flags, ws, st)))
@@ -542,10 +550,44 @@ extern "C" DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t 
         return n_fft == 8192 ? launch_big_fwd<8192>(x, y, g, mel, spec, ws, lp, st)
                              : launch_big_fwd<16384>(x, y, g, mel, spec, ws, lp, st);
     }
-#define CALL_FWD(LL, NGG) launch_fwd<LL, NGG>(x, y, g, mel, spec, ws, lp, st)
+#define CALL_FWD(LL, NGG) launch_fwd<LL, NGG>(x, y, dy, g, mel, spec, ws, lp, st)
     DMEL_DISPATCH(n_fft, lp.NG, CALL_FWD)
 #undef CALL_FWD
     return rc;
+}
+
+extern "C" DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
+                                int32_t win_length, int32_t n_fft, int32_t hop, int32_t n_mels,
+                                const dmel_melbank* bank, float log_eps, int32_t flags, float* y,
+                                void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    return forward_impl(x, batch, n_points, x_row_stride, lambda, win_length, n_fft, hop, n_mels, bank, log_eps, flags, y,
+                        nullptr, workspace, workspace_bytes, cuda_stream);
+}
+
+extern "C" DMEL_API int dmel_forward_jvp_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
+                                    float lambda, int32_t win_length, int32_t n_fft, int32_t hop, int32_t n_mels,
+                                    const dmel_melbank* bank, float log_eps, int32_t flags, float* y,
+                                    float* dy_dlambda, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    if (!dy_dlambda) return DMEL_ERR_NULL_POINTER;
+    return forward_impl(x, batch, n_points, x_row_stride, lambda, win_length, n_fft, hop, n_mels, bank, log_eps, flags, y,
+                        dy_dlambda, workspace, workspace_bytes, cuda_stream);
+}
+
+extern "C" DMEL_API int dmel_jvp_supported(int32_t n_fft) { const FftInfo fi = fft_info(n_fft); return (fi.ok && !fi.big) ? 1 : 0; }
+
+extern "C" DMEL_API int dmel_lambda_grad_f32(const float* grad_y, const float* dy_dlambda, int64_t count, float lambda,
+                                    float* grad_lambda, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    if (!grad_y || !dy_dlambda || !grad_lambda || !workspace) return DMEL_ERR_NULL_POINTER;
+    if (count <= 0) return DMEL_ERR_BAD_GEOMETRY;
+    if (workspace_bytes < sizeof(WsHeader)) return DMEL_ERR_WORKSPACE_TOO_SMALL;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const float sign = lambda > 0.f ? 1.f : (lambda < 0.f ? -1.f : 0.f);
+    long long blocks = (count / 4 + 255) / 256;
+    blocks = std::max<long long>(1, std::min<long long>(blocks, 4LL * NUM_SMS));
+    ProfScope prof(PROF_BWD, st);
+    dmel_lambda_grad_kernel<<<unsigned(blocks), 256, 0, st>>>(grad_y, dy_dlambda, count, sign,
+                                                              static_cast<WsHeader*>(workspace), grad_lambda);
+    return check_launch("dmel_lambda_grad_kernel");
 }
 
 extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,

@@ -119,6 +119,8 @@ dmel_prep_kernel(const float* __restrict__ x, long long x_stride, int B, int N, 
         ws.hdr->inv_norm = inv_norm;
         ws.hdr->left = left;
         ws.hdr->y_sum = 0.0;
+        ws.hdr->jvp_acc = 0.0;
+        ws.hdr->jvp_ticket = 0u;
     }
     __syncthreads();
     if (normalize) {
@@ -154,6 +156,39 @@ dmel_finalize_kernel(float* __restrict__ dx, int B, int N, int chunks_per_clip, 
         for (int i = (q_hi << 2) + threadIdx.x; i < hi; i += 256) dxb[i] -= mu;
     } else {
         for (int i = lo + threadIdx.x; i < hi; i += 256) dxb[i] -= mu;
+    }
+}
+
+// Backward of the JVP forward: dL/dlambda = sign(lambda) * sum(dL/dy * dy/d|lambda|).  One launch: every block adds
+// its fp64 partial, the last block to finish (ticket) converts the total and resets the accumulator for the next call.
+__global__ void __launch_bounds__(256)
+dmel_lambda_grad_kernel(const float* __restrict__ gy, const float* __restrict__ dy, long long n, float sign,
+                        WsHeader* hdr, float* __restrict__ grad_lambda) {
+    __shared__ double red[32];
+    __shared__ bool last;
+    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * 256;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const long long n4 = ((reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0 ? (n >> 2) : 0;
+    const float4* g4 = reinterpret_cast<const float4*>(gy);
+    const float4* d4 = reinterpret_cast<const float4*>(dy);
+    for (long long i = gid; i < n4; i += nthreads) {
+        const float4 a = __ldg(g4 + i), b = __ldg(d4 + i);
+        a0 = fmaf(a.x, b.x, a0); a1 = fmaf(a.y, b.y, a1); a2 = fmaf(a.z, b.z, a2); a3 = fmaf(a.w, b.w, a3);
+    }
+    for (long long i = (n4 << 2) + gid; i < n; i += nthreads) a0 = fmaf(__ldg(gy + i), __ldg(dy + i), a0);
+    const double tot = block_sum((double(a0) + double(a1)) + (double(a2) + double(a3)), red);
+    if (threadIdx.x == 0) {
+        atomicAdd(&hdr->jvp_acc, tot);
+        __threadfence();
+        last = atomicAdd(&hdr->jvp_ticket, 1u) == gridDim.x - 1;
+        if (last) {
+            __threadfence();
+            const double total = atomicAdd(&hdr->jvp_acc, 0.0);   // read through L2
+            *grad_lambda = float(double(sign) * total);
+            hdr->jvp_acc = 0.0;
+            hdr->jvp_ticket = 0u;
+        }
     }
 }
 

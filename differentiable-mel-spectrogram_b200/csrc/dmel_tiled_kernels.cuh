@@ -7,21 +7,30 @@ namespace dmel {
 
 // ----------------------------------------------------------------------------
 // forward (persistent: each CTA stages the constant tables once and walks tiles)
+//
+// JVP variant (the reference's training case: x is data, only lambd trains — models.py:19, main.py:27): instead of
+// two frames, one complex transform carries ONE frame windowed by w (real part) and by dw/d|lambda| (imaginary
+// part), i.e. X and X' = STFT(x * dw/dlambda); besides y it writes dy/d|lambda| = fb . 2Re(conj(X) X') (chain-ruled
+// through the fused log), so the backward collapses to the dot product sum(dL/dy * dy/dlambda): 1.0 instead of 1.5
+// complex transforms per frame for forward + backward, and nothing is recomputed.
 // ----------------------------------------------------------------------------
-template <int L, int NG, bool SPEC>
+template <int L, int NG, bool SPEC, bool JVP>
 __global__ void __launch_bounds__(NG * (L / Plan<L>::E), min_ctas(L, NG, NG * (L / Plan<L>::E)))
-dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelDev mel,
+dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ dy, Geom g, MelDev mel,
                 const float* __restrict__ win_g, const float2* __restrict__ tw_g, const float* __restrict__ means,
                 WsHeader* hdr) {
     constexpr int E = Plan<L>::E, GT = L / E, NT = NG * GT, TWN = TwTotal<L>::value;
     using P0 = Pass<L, 0>;
     extern __shared__ __align__(16) float smem_f[];
     const int TS = g.TT + 1;
-    const SmemLay lay = make_lay(L, NG, TWN, g.span, g.sub_span, g.M * TS, g.csr_ints, g.csr_floats, false, 1 + g.lookahead);
+    const int plane = round_up4(g.M * TS);   // JVP keeps two planes: mel and d(mel)/d|lambda|
+    const SmemLay lay = make_lay(L, NG, TWN, g.span, g.sub_span, JVP ? 2 * plane : g.M * TS, g.csr_ints, g.csr_floats, false,
+                                 1 + g.lookahead);
     float2* twt = reinterpret_cast<float2*>(smem_f + lay.twt);
     float* win = smem_f + lay.win;
     float* xs_sh = smem_f + lay.xs;
     float* tile = smem_f + lay.tile;
+    float* tile2 = tile + plane;
     int* csr_i = reinterpret_cast<int*>(smem_f + lay.csr_i);
     float* csr_w = smem_f + lay.csr_w;
 
@@ -31,6 +40,8 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
     const bool row_aligned = g.row_aligned != 0;
     const int tt_shift = ilog2(g.TT);
     const bool do_log = g.log_eps >= 0.f;
+    float inv_lam3 = 0.f, cprime = 0.f, centre = 0.f;
+    if (JVP) { inv_lam3 = hdr->inv_lam3; cprime = hdr->cprime; centre = hdr->centre; }
 
     // constant tables: once per CTA
     stage_table_async<NT>(smem_f + lay.twt, tw_g, 2 * TWN, tid);
@@ -81,7 +92,7 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
         }
 
         const int f_hi = min(grp * g.SF + g.SF, nfr);
-        for (int f = grp * g.SF; f < f_hi; f += 2) {
+        for (int f = grp * g.SF; f < f_hi; f += (JVP ? 1 : 2)) {
             const float* xa = xs + f * g.hop;
             const float* xb2 = xa + g.hop;
             float2 v[E];
@@ -92,7 +103,14 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
                 for (int r = 0; r < P0::R; ++r) {
                     const int n = j + r * P0::STR;
                     const float w = win[n];
-                    v[i * P0::R + r] = make_float2(xa[n] * w, xb2[n] * w);
+                    if (JVP) {
+                        // dw/d|lambda|[n] = w[n] * ((n-centre)^2/lambda^3 - cprime)
+                        const float d = float(n) - centre;
+                        const float xw = xa[n] * w;
+                        v[i * P0::R + r] = make_float2(xw, xw * fmaf(d * d, inv_lam3, -cprime));
+                    } else {
+                        v[i * P0::R + r] = make_float2(xa[n] * w, xb2[n] * w);
+                    }
                 }
             }
             run_passes<L, 0, true>(v, buf, twt, gtid, bar_id);
@@ -103,10 +121,13 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
                 const float2 z2 = buf[(L - k) & (L - 1)];
                 const float ar = 0.5f * (z1.x + z2.x), ai = 0.5f * (z1.y - z2.y);
                 const float br = 0.5f * (z1.y + z2.y), bi = 0.5f * (z2.x - z1.x);
-                const float pa = fmaf(ar, ar, ai * ai), pb = fmaf(br, br, bi * bi);
+                // pair: both powers.  JVP: (ar,ai) = X, (br,bi) = X' -> P = |X|^2, dP/d|lambda| = 2 Re(conj(X) X')
+                const float pa = fmaf(ar, ar, ai * ai);
+                const float pb = JVP ? 2.f * fmaf(ar, br, ai * bi) : fmaf(br, br, bi * bi);
                 if (SPEC) {
                     tile[k * TS + f] = pa;
-                    tile[k * TS + f + 1] = pb;
+                    if (JVP) tile2[k * TS + f] = pb;
+                    else tile[k * TS + f + 1] = pb;
                 } else {
                     buf[k] = make_float2(pa, pb);
                 }
@@ -131,17 +152,24 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, MelD
                         sa = fmaf(w.w, a3.x, sa); sb = fmaf(w.w, a3.y, sb);
                     }
                     tile[m * TS + f] = sa;
-                    tile[m * TS + f + 1] = sb;
+                    if (JVP) tile2[m * TS + f] = sb;
+                    else tile[m * TS + f + 1] = sb;
                 }
             }
         }
         __syncthreads();
         // models.py:54 pack into (B,1,M,T), T fastest; optional fused log (models.py:72-73)
         float* yb = y + (long long)b * g.M * g.T + t0;
+        float* dyb = JVP ? dy + (long long)b * g.M * g.T + t0 : nullptr;
         for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
             const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
             if (tt < nfr) {
                 float val = tile[m * TS + tt];
+                if (JVP) {
+                    // d log(mel + eps) / d|lambda| = dmel / (mel + eps)
+                    const float dv = tile2[m * TS + tt];
+                    dyb[(long long)m * g.T + tt] = do_log ? __fdividef(dv, val + g.log_eps) : dv;
+                }
                 // lg2.approx * ln2: <= 3 ulp, i.e. ~1e-6 absolute on log-mel values (budget 1e-5 + 1e-4 |y|)
                 if (do_log) val = __logf(val + g.log_eps);
                 yb[(long long)m * g.T + tt] = val;

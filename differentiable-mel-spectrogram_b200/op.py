@@ -11,6 +11,7 @@ in libdmel_b200.so.  Non-CUDA tensors are rejected (no CPU fallback).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -95,6 +96,10 @@ class _on_device:
         return False
 
 
+# lambda-only training steps use the forward-mode (JVP) kernel; set False (or DMEL_NO_JVP=1) to always recompute in
+# the backward instead (cheaper forwards when most of them are never back-propagated, e.g. long validation loops).
+USE_JVP = os.environ.get("DMEL_NO_JVP", "0") != "1"
+
 _ws_bytes_cache: dict = {}
 _Y_SUM_OFFSET = [-1]
 
@@ -114,18 +119,30 @@ class DmelFunction(torch.autograd.Function):
         if ws_bytes is None:
             ws_bytes = _ws_bytes_cache[wkey] = lib.dmel_workspace_bytes(geo.batch, geo.n_fft)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        # The reference's training case: x is data, only lambd trains (models.py:19, main.py:27).  Then dy/dlambda is
+        # produced by the forward itself (derivative-window STFT) and the backward is a dot product.
+        jvp = (USE_JVP and ctx.needs_input_grad[1] and not ctx.needs_input_grad[0] and bool(lib.dmel_jvp_supported(geo.n_fft)))
+        dy = torch.empty_like(y) if jvp else None
+        bank_ref = bank.ref() if bank is not None else None
         with _on_device(dev):
-            rc = lib.dmel_forward_f32(
-                x.data_ptr(), geo.batch, geo.n_points, x.stride(0),
-                lam_value, geo.win_length, geo.n_fft, geo.hop,
-                geo.n_mels, bank.ref() if bank is not None else None, float(log_eps),
-                int(flags), y.data_ptr(),
-                ws.data_ptr(), ws_bytes, _stream_ptr(dev))
-        _lib.check(rc, "dmel_forward_f32")
+            if jvp:
+                rc = lib.dmel_forward_jvp_f32(
+                    x.data_ptr(), geo.batch, geo.n_points, x.stride(0), lam_value, geo.win_length, geo.n_fft, geo.hop,
+                    geo.n_mels, bank_ref, float(log_eps), int(flags), y.data_ptr(), dy.data_ptr(),
+                    ws.data_ptr(), ws_bytes, _stream_ptr(dev))
+            else:
+                rc = lib.dmel_forward_f32(
+                    x.data_ptr(), geo.batch, geo.n_points, x.stride(0), lam_value, geo.win_length, geo.n_fft, geo.hop,
+                    geo.n_mels, bank_ref, float(log_eps), int(flags), y.data_ptr(),
+                    ws.data_ptr(), ws_bytes, _stream_ptr(dev))
+        _lib.check(rc, "dmel_forward_jvp_f32" if jvp else "dmel_forward_f32")
         ctx.geo, ctx.bank, ctx.log_eps, ctx.flags, ctx.lam_value = geo, bank, float(log_eps), int(flags), lam_value
         ctx.ws = ws
+        ctx.jvp = jvp
         ctx.lambd_shape, ctx.lambd_dtype = lambd.shape, lambd.dtype
-        if log_eps >= 0:
+        if jvp:
+            ctx.save_for_backward(dy)
+        elif log_eps >= 0:
             ctx.save_for_backward(x, y)
         else:
             ctx.save_for_backward(x)
@@ -143,14 +160,23 @@ class DmelFunction(torch.autograd.Function):
         lib = _lib.load()
         geo = ctx.geo
         saved = ctx.saved_tensors
+        gy = grad_y.to(torch.float32).contiguous()
+        ws = ctx.ws
+        if ctx.jvp:
+            dy = saved[0]
+            dev = dy.device
+            grad_lambda = torch.empty((), dtype=torch.float32, device=dev)
+            with _on_device(dev):
+                rc = lib.dmel_lambda_grad_f32(gy.data_ptr(), dy.data_ptr(), gy.numel(), ctx.lam_value, grad_lambda.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+            _lib.check(rc, "dmel_lambda_grad_f32")
+            return None, grad_lambda.reshape(ctx.lambd_shape).to(ctx.lambd_dtype), None, None, None, None, None
         x = saved[0]
         y = saved[1] if ctx.log_eps >= 0 else None
         dev = x.device
         need_dx = ctx.needs_input_grad[0]
-        gy = grad_y.to(torch.float32).contiguous()
         grad_x = torch.empty((geo.batch, geo.n_points), dtype=torch.float32, device=dev) if need_dx else None
         grad_lambda = torch.empty((), dtype=torch.float32, device=dev)
-        ws = ctx.ws
         with _on_device(dev):
             rc = lib.dmel_backward_f32(
                 x.data_ptr(), geo.batch, geo.n_points, x.stride(0),

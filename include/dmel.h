@@ -118,6 +118,24 @@ DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t n_points, i
                      int32_t flags, float* y,
                      void* workspace, size_t workspace_bytes, void* cuda_stream);
 
+/* Forward-mode variant for the reference's training case (x is data, only `lambd` trains: models.py:19,
+ * main.py:27).  Same arguments and the same y as dmel_forward_f32, plus dy_dlambda [batch,1,rows,T]:
+ * d y / d|lambda| from the derivative-window STFT, 2 Re(conj(X) . STFT(x * dw/dlambda)), mel-projected and
+ * chain-ruled through the fused log.  Costs one complex FFT per frame instead of a half, and makes the
+ * backward a dot product (dmel_lambda_grad_f32): 1.0 instead of 1.5 FFTs per frame per training step, no
+ * recomputation.  Tiled FFT path only (dmel_jvp_supported: n_fft 128..4096).                              */
+DMEL_API int dmel_jvp_supported(int32_t n_fft);
+DMEL_API int dmel_forward_jvp_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
+                         float lambda, int32_t win_length, int32_t n_fft, int32_t hop,
+                         int32_t n_mels, const dmel_melbank* bank, float log_eps,
+                         int32_t flags, float* y, float* dy_dlambda,
+                         void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* dL/dlambda = sign(lambda) * sum_i grad_y[i] * dy_dlambda[i]  (count = batch*rows*T), one fp32 out;
+ * workspace = the one dmel_forward_jvp_f32 filled (its header holds the self-resetting fp64 accumulator). */
+DMEL_API int dmel_lambda_grad_f32(const float* grad_y, const float* dy_dlambda, int64_t count, float lambda,
+                         float* grad_lambda, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
 /* Backward of the same chain (what autograd does for train.py:47).
  *   y            forward output; read only when log_eps >= 0 (may be NULL otherwise)
  *   grad_y       dL/dy, same shape as y
