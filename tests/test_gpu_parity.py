@@ -194,7 +194,8 @@ def test_full_size_properties_esc50_and_large_batch(cuda_device):
         ll.grad = None
         for sl in (slice(0, h), slice(h, B)):
             (dm.dmel(x[sl], ll, log_eps=EPS, **kw) * G[sl]).sum().backward()
-        assert abs(float(ll.grad) - whole) <= 1e-5 * abs(whole)
+        # (the shards take the forward-mode kernel since their x carries no grad: same derivative, frequency-domain form)
+        assert abs(float(ll.grad) - whole) <= 2e-4 * abs(whole)
         assert float(dx.mean(dim=1).abs().max()) <= 1e-4 * float(dx.abs().max())
         # (e) a few clips against the oracle
         sub = [0, B // 2, B - 1]
