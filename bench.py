@@ -228,6 +228,7 @@ def main():
     ap.add_argument("--workload", default="audio_mnist")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch the resident loop eagerly instead of from a CUDA graph")
+    ap.add_argument("--nccl-only", action="store_true", help="use NCCL for the lambda-gradient all-reduce (default: peer-memory kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
@@ -293,12 +294,22 @@ def main():
                                    wss[s].data_ptr(), ws_bytes, 1, st)
         assert rc == 0, lib.dmel_status_string(rc)
         if world > 1:
-            dist.all_reduce(dls[s])            # the path's only collective: sum of the scalar lambda gradient
+            # the path's only collective: sum of the scalar lambda gradient
+            if ring is not None:
+                ring.all_reduce_(dls[s].view(1))   # one-shot exchange over NVLink peer memory
+            else:
+                dist.all_reduce(dls[s])            # NCCL
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    ring = None
+    if world > 1 and not args.nccl_only:
+        ring = dm.PeerRing.create(dev)
+        if rank == 0 and ring is None:
+            print("[bench] peer-memory all-reduce unavailable or failed its self-test: using NCCL", file=sys.stderr)
 
     # warm-up (eager), then optional graph capture of one rotation
     for i in range(args.warmup):
@@ -509,7 +520,9 @@ def main():
             "config": config_dict(args, w, extra={
                 "l2_policy": f"inputs rotate over {R} buffer sets ({R * set_bytes / 2**20:.0f} MiB > 2x L2)",
                 "launch": "cuda_graph" if graph is not None else "eager",
-                "collective": "nccl all_reduce(dL/dlambda, 1 x fp32) per step" if world > 1 else "none (1 GPU)"}),
+                "collective": ("none (1 GPU)" if world == 1 else
+                               "one-shot all-reduce of dL/dlambda (1 x fp32) over NVLink peer memory, in the step" if ring is not None
+                               else "nccl all_reduce(dL/dlambda, 1 x fp32) per step")}),
             "gpu_launches": gpu_launches,
             "kernels_ms": {k: round(v[0], 6) for k, v in kern.items()},
             "lambda_only": {"ms_per_step": ms_lambda_only, "value": audio_s / (ms_lambda_only * 1e-3), "unit": UNIT,

@@ -7,7 +7,7 @@ identifier).  Public surface = the reference's own: `MelSpectrogramLayer`, `Spec
 """
 from . import _lib
 from ._lib import DmelError, build, load
-from .dist import allreduce_lambda_grad, broadcast_lambda, shard_bounds
+from .dist import PeerRing, allreduce_lambda_grad, broadcast_lambda, shard_bounds
 from .layers import MelSpectrogramLayer, SpectrogramLayer
 from .melbank import melscale_fbanks_htk, pack_bank
 from .op import dmel, next_power_of_2, query_launch, resolve_geometry, shift_bit_length, window_length_from_lambda
@@ -17,5 +17,5 @@ __all__ = [
     "MelSpectrogramLayer", "SpectrogramLayer", "dmel", "differentiable_spectrogram",
     "differentiable_gaussian_window", "next_power_of_2", "shift_bit_length", "window_length_from_lambda",
     "resolve_geometry", "query_launch", "melscale_fbanks_htk", "pack_bank", "allreduce_lambda_grad",
-    "broadcast_lambda", "shard_bounds", "DmelError", "build", "load",
+    "broadcast_lambda", "shard_bounds", "PeerRing", "DmelError", "build", "load",
 ]

@@ -31,6 +31,8 @@ EXPORTED_SYMBOLS = (
     "dmel_lambda_grad_f32",
     "dmel_backward_f32",
     "dmel_query_launch",
+    "dmel_peer_buffer_bytes",
+    "dmel_peer_allreduce_f32",
     "dmel_launch_count",
     "dmel_profile_enable",
     "dmel_profile_read",
@@ -109,6 +111,10 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.dmel_lambda_grad_f32.restype = c.c_int
     lib.dmel_lambda_grad_f32.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_float, c.c_void_p, c.c_void_p, c.c_size_t,
                                          c.c_void_p]
+    lib.dmel_peer_buffer_bytes.restype = c.c_size_t
+    lib.dmel_peer_buffer_bytes.argtypes = [c.c_int32]
+    lib.dmel_peer_allreduce_f32.restype = c.c_int
+    lib.dmel_peer_allreduce_f32.argtypes = [c.c_void_p, c.c_void_p, c.c_int32, c.c_int32, c.c_void_p]
     lib.dmel_backward_f32.restype = c.c_int
     lib.dmel_backward_f32.argtypes = [
         c.c_void_p, c.c_int64, c.c_int64, c.c_int64,

@@ -7,10 +7,12 @@ ordinary parameter and DDP's bucket all-reduce covers it.
 """
 from __future__ import annotations
 
-from typing import Iterable, Tuple
+from typing import Iterable, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 def shard_bounds(n_clips: int, world_size: int, rank: int) -> Tuple[int, int]:
@@ -49,3 +51,71 @@ def broadcast_lambda(params: Iterable[torch.nn.Parameter], src: int = 0, group=N
         return
     for p in params:
         dist.broadcast(p.data, src=src, group=group)
+
+
+class PeerRing:
+    """One-shot all-reduce of one fp32 over NVLink peer memory (include/dmel.h, dmel_peer_allreduce_f32).
+
+    Every rank allocates a small zeroed buffer, the buffers are exchanged as CUDA-IPC handles through the
+    process group, and the kernel then talks to all peers directly (stores + system-scope release/acquire flags)
+    — one 32-thread launch instead of an NCCL call whose latency (~20 us at 8 ranks) is a fifth of a small
+    DMEL step.  All ranks of the group must be GPUs of one box with peer access.  `PeerRing.create()` returns
+    None (callers keep using NCCL) when the setup or its self-test against the group's all_reduce fails.
+    """
+
+    def __init__(self, device: torch.device, group=None):
+        from torch.multiprocessing.reductions import reduce_tensor
+        lib = _lib.load()
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = torch.device(device)
+        nbytes = lib.dmel_peer_buffer_bytes(self.world)
+        if nbytes == 0:
+            raise _lib.DmelError(f"peer ring supports at most 32 ranks, got {self.world}")
+        self.buf = torch.zeros(nbytes // 4, dtype=torch.int32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        rebuild, args = reduce_tensor(self.buf)                       # CUDA IPC handle of our buffer
+        gathered: List[Optional[tuple]] = [None] * self.world
+        dist.all_gather_object(gathered, args, group=group)
+        self.peers = [self.buf if r == self.rank else rebuild(*gathered[r]) for r in range(self.world)]
+        self.bases = torch.tensor([t.data_ptr() for t in self.peers], dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
+
+    def all_reduce_(self, value: torch.Tensor) -> torch.Tensor:
+        """In-place sum over the ranks of a 1-element fp32 CUDA tensor, on the current stream."""
+        if value.numel() != 1 or value.dtype != torch.float32 or value.device != self.device:
+            raise ValueError("PeerRing reduces one fp32 element on its own device")
+        lib = _lib.load()
+        st = int(torch._C._cuda_getCurrentRawStream(self.device.index))
+        _lib.check(lib.dmel_peer_allreduce_f32(value.data_ptr(), self.bases.data_ptr(), self.rank, self.world, st),
+                   "dmel_peer_allreduce_f32")
+        return value
+
+    def timed_out(self) -> bool:
+        return bool(int(self.buf[4 * self.world + 1]))
+
+    @staticmethod
+    def create(device: torch.device, group=None, trials: int = 4) -> Optional["PeerRing"]:
+        """Build a ring and check it against the group's own all_reduce; None if anything is off."""
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) < 2:
+            return None
+        ok = torch.ones(1, device=device)
+        ring = None
+        try:
+            ring = PeerRing(device, group)
+            g = torch.Generator(device=device).manual_seed(17 + ring.rank)
+            for _ in range(trials):
+                v = torch.randn(1, device=device, generator=g)
+                want = v.clone()
+                dist.all_reduce(want, group=group)
+                got = ring.all_reduce_(v.clone())
+                torch.cuda.synchronize(device)
+                if ring.timed_out() or not torch.isfinite(got).all() or abs(float(got) - float(want)) > 1e-5 * max(1.0, abs(float(want))):
+                    ok.zero_()
+                    break
+        except Exception:
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)       # all ranks agree on the outcome
+        return ring if bool(ok.item()) and ring is not None else None

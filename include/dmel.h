@@ -152,6 +152,17 @@ DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t n_points, 
                       void* workspace, size_t workspace_bytes, int32_t prepared,
                       void* cuda_stream);
 
+/* The path's only collective — sum of the scalar dL/dlambda over the GPUs of one box — as a one-shot exchange
+ * over NVLink peer memory instead of an NCCL call.  Each rank allocates dmel_peer_buffer_bytes(world) of zeroed
+ * device memory, maps every peer's buffer into its own address space (CUDA IPC) and passes the `world` base
+ * pointers (its own at index `rank`) as a DEVICE array of 64-bit addresses.  `value` (device, 1 x fp32) is replaced
+ * by the sum, bit-identical on all ranks (summed in rank order).  Stream-ordered, graph-capturable; every rank must
+ * make the same sequence of calls.  On a peer timeout (~0.25 s) the result is NaN and word [4*world+1] of the
+ * rank's buffer is set to 1.  dist.py (PeerRing) is the host side; NCCL remains the fallback.                     */
+DMEL_API size_t dmel_peer_buffer_bytes(int32_t world);
+DMEL_API int dmel_peer_allreduce_f32(float* value, const void* peer_bases_dev, int32_t rank, int32_t world,
+                            void* cuda_stream);
+
 /* Introspection for tests / benchmarks: tile size (frames per CTA), FFT groups per CTA,
  * dynamic shared memory and threads per CTA the launcher would pick.  rows = n_mels or
  * n_fft/2+1; bank_nnz = entries of the sparse bank form that pass stages (0 in spectrogram
