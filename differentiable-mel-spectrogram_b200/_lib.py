@@ -33,6 +33,11 @@ EXPORTED_SYMBOLS = (
     "dmel_query_launch",
     "dmel_peer_buffer_bytes",
     "dmel_peer_allreduce_f32",
+    "dmel_peer_alloc",
+    "dmel_peer_open",
+    "dmel_peer_close",
+    "dmel_peer_free",
+    "dmel_peer_timed_out",
     "dmel_launch_count",
     "dmel_profile_enable",
     "dmel_profile_read",
@@ -113,6 +118,16 @@ def _declare(lib: ctypes.CDLL) -> None:
                                          c.c_void_p]
     lib.dmel_peer_buffer_bytes.restype = c.c_size_t
     lib.dmel_peer_buffer_bytes.argtypes = [c.c_int32]
+    lib.dmel_peer_alloc.restype = c.c_int
+    lib.dmel_peer_alloc.argtypes = [c.c_int32, c.POINTER(c.c_void_p), c.c_char_p]
+    lib.dmel_peer_open.restype = c.c_int
+    lib.dmel_peer_open.argtypes = [c.c_char_p, c.POINTER(c.c_void_p)]
+    lib.dmel_peer_close.restype = c.c_int
+    lib.dmel_peer_close.argtypes = [c.c_void_p]
+    lib.dmel_peer_free.restype = c.c_int
+    lib.dmel_peer_free.argtypes = [c.c_void_p]
+    lib.dmel_peer_timed_out.restype = c.c_int
+    lib.dmel_peer_timed_out.argtypes = [c.c_void_p, c.c_int32, c.POINTER(c.c_int32)]
     lib.dmel_peer_allreduce_f32.restype = c.c_int
     lib.dmel_peer_allreduce_f32.argtypes = [c.c_void_p, c.c_void_p, c.c_int32, c.c_int32, c.c_void_p]
     lib.dmel_backward_f32.restype = c.c_int

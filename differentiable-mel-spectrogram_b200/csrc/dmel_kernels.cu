@@ -37,6 +37,7 @@
 
 #include <stddef.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <atomic>
@@ -709,4 +710,57 @@ extern "C" DMEL_API int dmel_peer_allreduce_f32(float* value, const void* peer_b
     dmel_peer_allreduce_kernel<<<1, 32, 0, st>>>(value, static_cast<const long long*>(peer_bases_dev), rank, world,
                                                   500000000LL);
     return check_launch("dmel_peer_allreduce_kernel");
+}
+
+// ---- symmetric buffers for the peer all-reduce: raw cudaMalloc (IPC handles refer to whole allocations) owned by
+// the caller through these explicit calls; peers are mapped into the CURRENT device's context with peer access.
+extern "C" DMEL_API int dmel_peer_alloc(int32_t world, void** buffer, unsigned char* ipc_handle_64) {
+    if (!buffer || !ipc_handle_64) return DMEL_ERR_NULL_POINTER;
+    const size_t bytes = dmel_peer_buffer_bytes(world);
+    if (bytes == 0) return DMEL_ERR_BAD_GEOMETRY;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return check_launch("cudaMalloc(peer buffer)") ? DMEL_ERR_LAUNCH_FAILED : DMEL_ERR_LAUNCH_FAILED;
+    if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaFree(p); return check_launch("cudaMemset(peer buffer)") ? DMEL_ERR_LAUNCH_FAILED : DMEL_ERR_LAUNCH_FAILED; }
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaFree(p); (void)check_launch("cudaIpcGetMemHandle"); return DMEL_ERR_LAUNCH_FAILED; }
+    memcpy(ipc_handle_64, &h, 64);
+    *buffer = p;
+    return DMEL_OK;
+}
+
+extern "C" DMEL_API int dmel_peer_open(const unsigned char* ipc_handle_64, void** mapped) {
+    if (!ipc_handle_64 || !mapped) return DMEL_ERR_NULL_POINTER;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle_64, 64);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        (void)check_launch("cudaIpcOpenMemHandle");
+        return DMEL_ERR_LAUNCH_FAILED;
+    }
+    *mapped = p;
+    return DMEL_OK;
+}
+
+extern "C" DMEL_API int dmel_peer_close(void* mapped) {
+    if (!mapped) return DMEL_OK;
+    return cudaIpcCloseMemHandle(mapped) == cudaSuccess ? DMEL_OK : DMEL_ERR_LAUNCH_FAILED;
+}
+
+extern "C" DMEL_API int dmel_peer_free(void* buffer) {
+    if (!buffer) return DMEL_OK;
+    return cudaFree(buffer) == cudaSuccess ? DMEL_OK : DMEL_ERR_LAUNCH_FAILED;
+}
+
+// synchronous read of the rank's own error word (1 after a peer timeout); for self-tests, not for the hot path
+extern "C" DMEL_API int dmel_peer_timed_out(const void* buffer, int32_t world, int32_t* timed_out) {
+    if (!buffer || !timed_out) return DMEL_ERR_NULL_POINTER;
+    if (dmel_peer_buffer_bytes(world) == 0) return DMEL_ERR_BAD_GEOMETRY;
+    int v = 0;
+    if (cudaMemcpy(&v, static_cast<const int*>(buffer) + 4 * world + 1, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        (void)check_launch("cudaMemcpy(peer status)");
+        return DMEL_ERR_LAUNCH_FAILED;
+    }
+    *timed_out = v;
+    return DMEL_OK;
 }

@@ -64,24 +64,46 @@ class PeerRing:
     """
 
     def __init__(self, device: torch.device, group=None):
-        from torch.multiprocessing.reductions import reduce_tensor
+        import ctypes
         lib = _lib.load()
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.device = torch.device(device)
-        nbytes = lib.dmel_peer_buffer_bytes(self.world)
-        if nbytes == 0:
+        self._mapped: List[int] = []
+        self._own = 0
+        if lib.dmel_peer_buffer_bytes(self.world) == 0:
             raise _lib.DmelError(f"peer ring supports at most 32 ranks, got {self.world}")
-        self.buf = torch.zeros(nbytes // 4, dtype=torch.int32, device=self.device)
-        torch.cuda.synchronize(self.device)
-        rebuild, args = reduce_tensor(self.buf)                       # CUDA IPC handle of our buffer
-        gathered: List[Optional[tuple]] = [None] * self.world
-        dist.all_gather_object(gathered, args, group=group)
-        self.peers = [self.buf if r == self.rank else rebuild(*gathered[r]) for r in range(self.world)]
-        self.bases = torch.tensor([t.data_ptr() for t in self.peers], dtype=torch.int64, device=self.device)
-        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            own = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            _lib.check(lib.dmel_peer_alloc(self.world, ctypes.byref(own), handle), "dmel_peer_alloc")
+            self._own = own.value
+            gathered: List[Optional[bytes]] = [None] * self.world
+            dist.all_gather_object(gathered, handle.raw, group=group)
+            bases = []
+            for r in range(self.world):
+                if r == self.rank:
+                    bases.append(self._own)
+                    continue
+                mapped = ctypes.c_void_p()
+                _lib.check(lib.dmel_peer_open(gathered[r], ctypes.byref(mapped)), "dmel_peer_open")
+                self._mapped.append(mapped.value)
+                bases.append(mapped.value)
+            self.bases = torch.tensor(bases, dtype=torch.int64, device=self.device)
+            torch.cuda.synchronize(self.device)
         dist.barrier(group=group)
+
+    def close(self) -> None:
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for m in self._mapped:
+                lib.dmel_peer_close(m)
+            self._mapped = []
+            if self._own:
+                lib.dmel_peer_free(self._own)
+                self._own = 0
 
     def all_reduce_(self, value: torch.Tensor) -> torch.Tensor:
         """In-place sum over the ranks of a 1-element fp32 CUDA tensor, on the current stream."""
@@ -94,7 +116,12 @@ class PeerRing:
         return value
 
     def timed_out(self) -> bool:
-        return bool(int(self.buf[4 * self.world + 1]))
+        """True if any call so far gave up waiting for a peer (its result was NaN). Synchronises the device."""
+        import ctypes
+        flag = ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().dmel_peer_timed_out(self._own, self.world, ctypes.byref(flag)), "dmel_peer_timed_out")
+        return flag.value != 0
 
     @staticmethod
     def create(device: torch.device, group=None, trials: int = 4) -> Optional["PeerRing"]:

@@ -160,6 +160,15 @@ DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t n_points, 
  * make the same sequence of calls.  On a peer timeout (~0.25 s) the result is NaN and word [4*world+1] of the
  * rank's buffer is set to 1.  dist.py (PeerRing) is the host side; NCCL remains the fallback.                     */
 DMEL_API size_t dmel_peer_buffer_bytes(int32_t world);
+/* The symmetric buffers are whole cudaMalloc allocations (that is what a CUDA IPC handle names), owned by the
+ * caller through these four calls: alloc (zeroed, returns the 64-byte IPC handle to ship to the peers), open (map a
+ * peer's handle into the current device's context, peer access enabled), close, free.                            */
+DMEL_API int dmel_peer_alloc(int32_t world, void** buffer, unsigned char* ipc_handle_64);
+DMEL_API int dmel_peer_open(const unsigned char* ipc_handle_64, void** mapped);
+DMEL_API int dmel_peer_close(void* mapped);
+DMEL_API int dmel_peer_free(void* buffer);
+/* synchronous read of the rank's own error word (self-tests only) */
+DMEL_API int dmel_peer_timed_out(const void* buffer, int32_t world, int32_t* timed_out);
 DMEL_API int dmel_peer_allreduce_f32(float* value, const void* peer_bases_dev, int32_t rank, int32_t world,
                             void* cuda_stream);
 
