@@ -289,15 +289,20 @@ def main():
         rc = lib.dmel_forward_f32(xs[s].data_ptr(), B, N, N, lam, geo.win_length, geo.n_fft, hop, M, bank.ref(), LOG_EPS, 0,
                                   ys[s].data_ptr(), wss[s].data_ptr(), ws_bytes, st)
         assert rc == 0, lib.dmel_status_string(rc)
-        rc = lib.dmel_backward_f32(xs[s].data_ptr(), B, N, N, lam, geo.win_length, geo.n_fft, hop, M, bank.ref(), LOG_EPS, 0,
-                                   ys[s].data_ptr(), Gs[s].data_ptr(), dxs[s].data_ptr(), dls[s].data_ptr(),
-                                   wss[s].data_ptr(), ws_bytes, 1, st)
-        assert rc == 0, lib.dmel_status_string(rc)
-        if world > 1:
-            # the path's only collective: sum of the scalar lambda gradient
-            if ring is not None:
-                ring.all_reduce_(dls[s].view(1))   # one-shot exchange over NVLink peer memory
-            else:
+        # the path's only collective is the sum of the scalar lambda gradient over the GPUs
+        if ring is not None:
+            # fused: the backward's finalize kernel exchanges the scalar over NVLink peer memory
+            rc = lib.dmel_backward_allreduce_f32(xs[s].data_ptr(), B, N, N, lam, geo.win_length, geo.n_fft, hop, M, bank.ref(),
+                                                 LOG_EPS, 0, ys[s].data_ptr(), Gs[s].data_ptr(), dxs[s].data_ptr(),
+                                                 dls[s].data_ptr(), wss[s].data_ptr(), ws_bytes, 1, st,
+                                                 ring.bases.data_ptr(), rank, world)
+            assert rc == 0, lib.dmel_status_string(rc)
+        else:
+            rc = lib.dmel_backward_f32(xs[s].data_ptr(), B, N, N, lam, geo.win_length, geo.n_fft, hop, M, bank.ref(), LOG_EPS, 0,
+                                       ys[s].data_ptr(), Gs[s].data_ptr(), dxs[s].data_ptr(), dls[s].data_ptr(),
+                                       wss[s].data_ptr(), ws_bytes, 1, st)
+            assert rc == 0, lib.dmel_status_string(rc)
+            if world > 1:
                 dist.all_reduce(dls[s])            # NCCL
 
     def barrier():
@@ -437,7 +442,7 @@ def main():
                     y = layer(xin)
                     y.backward(Gs[j % R])
                     if world > 1:
-                        dm.allreduce_lambda_grad([layer.lambd])
+                        dm.allreduce_lambda_grad([layer.lambd], ring=ring)
                     free[j % 2].record(main_stream)
                     # the step's scalar results go back to the host: dL/dlambda and one checksum element of dL/dx
                     host_out[j % 2, 0].copy_(layer.lambd.grad, non_blocking=True)
@@ -521,7 +526,7 @@ def main():
                 "l2_policy": f"inputs rotate over {R} buffer sets ({R * set_bytes / 2**20:.0f} MiB > 2x L2)",
                 "launch": "cuda_graph" if graph is not None else "eager",
                 "collective": ("none (1 GPU)" if world == 1 else
-                               "one-shot all-reduce of dL/dlambda (1 x fp32) over NVLink peer memory, in the step" if ring is not None
+                               "all-reduce of dL/dlambda (1 x fp32) fused into the backward's finalize kernel over NVLink peer memory" if ring is not None
                                else "nccl all_reduce(dL/dlambda, 1 x fp32) per step")}),
             "gpu_launches": gpu_launches,
             "kernels_ms": {k: round(v[0], 6) for k, v in kern.items()},
@@ -536,6 +541,8 @@ def main():
                          "step_frac": algorithmic_bytes(w, "step") / (step_ms * 1e-3) / 1e9 / peak},
             "clocks": clocks,
         }
+        if ring is not None:
+            line["collective_timed_out"] = ring.timed_out()
         if e2e:
             line["e2e"] = {"value": world * audio_s * e2e[1] / (e2e[0] * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": 4 * B * N, "d2h_bytes_per_step": 8, "steps": e2e[1],

@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "dmel_jvp_supported",
     "dmel_lambda_grad_f32",
     "dmel_backward_f32",
+    "dmel_backward_allreduce_f32",
     "dmel_query_launch",
     "dmel_peer_buffer_bytes",
     "dmel_peer_allreduce_f32",
@@ -139,6 +140,8 @@ def _declare(lib: ctypes.CDLL) -> None:
         c.c_void_p, c.c_void_p,                               # grad_x, grad_lambda
         c.c_void_p, c.c_size_t, c.c_int32, c.c_void_p,        # workspace, bytes, prepared, stream
     ]
+    lib.dmel_backward_allreduce_f32.restype = c.c_int
+    lib.dmel_backward_allreduce_f32.argtypes = lib.dmel_backward_f32.argtypes + [c.c_void_p, c.c_int32, c.c_int32]
     lib.dmel_query_launch.restype = c.c_int
     lib.dmel_query_launch.argtypes = [
         c.c_int64, c.c_int64, c.c_int32, c.c_int32, c.c_int32, c.c_int32, c.c_int32,

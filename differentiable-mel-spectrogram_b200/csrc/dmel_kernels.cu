@@ -59,6 +59,9 @@ namespace dmel {
 // host side: planning + dispatch
 // ----------------------------------------------------------------------------
 constexpr size_t SMEM_MAX = 227 * 1024;
+// peer all-reduce spin bound, ~2 s at 2 GHz: far beyond any healthy skew between ranks (graph instantiation,
+// first touch), short enough never to look like a hang
+static constexpr long long PEER_TIMEOUT_CYCLES = 4000000000LL;
 constexpr int NUM_SMS = 148;
 
 template <int L> static PlanDesc plan_desc_of() {
@@ -591,11 +594,11 @@ extern "C" DMEL_API int dmel_lambda_grad_f32(const float* grad_y, const float* d
     return check_launch("dmel_lambda_grad_kernel");
 }
 
-extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
-                                 int32_t win_length, int32_t n_fft, int32_t hop, int32_t n_mels,
-                                 const dmel_melbank* bank, float log_eps, int32_t flags, const float* y,
-                                 const float* grad_y, float* grad_x, float* grad_lambda, void* workspace,
-                                 size_t workspace_bytes, int32_t prepared, void* cuda_stream) {
+static int backward_impl(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
+                         int32_t win_length, int32_t n_fft, int32_t hop, int32_t n_mels, const dmel_melbank* bank,
+                         float log_eps, int32_t flags, const float* y, const float* grad_y, float* grad_x,
+                         float* grad_lambda, void* workspace, size_t workspace_bytes, int32_t prepared,
+                         void* cuda_stream, const void* peer_bases_dev, int32_t rank, int32_t world) {
     if (!grad_y || !grad_lambda) return DMEL_ERR_NULL_POINTER;
     if (log_eps >= 0.f && !y) return DMEL_ERR_NULL_POINTER;
     int rc = validate(x, batch, n_points, x_row_stride, win_length, n_fft, hop, n_mels, bank, workspace, workspace_bytes);
@@ -659,8 +662,32 @@ extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t
     if (!csum) grid = 1;
     ProfScope prof(PROF_FINALIZE, st);
     dmel_finalize_kernel<<<unsigned(grid), 256, 0, st>>>(grad_x, int(batch), int(n_points), chunks, csum, ws.hdr,
-                                                         sign, grad_lambda);
+                                                         sign, grad_lambda, static_cast<const long long*>(peer_bases_dev),
+                                                         rank, world, PEER_TIMEOUT_CYCLES);
     return check_launch("dmel_finalize_kernel");
+}
+
+extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
+                                 int32_t win_length, int32_t n_fft, int32_t hop, int32_t n_mels,
+                                 const dmel_melbank* bank, float log_eps, int32_t flags, const float* y,
+                                 const float* grad_y, float* grad_x, float* grad_lambda, void* workspace,
+                                 size_t workspace_bytes, int32_t prepared, void* cuda_stream) {
+    return backward_impl(x, batch, n_points, x_row_stride, lambda, win_length, n_fft, hop, n_mels, bank, log_eps, flags, y,
+                         grad_y, grad_x, grad_lambda, workspace, workspace_bytes, prepared, cuda_stream, nullptr, 0, 1);
+}
+
+extern "C" DMEL_API int dmel_backward_allreduce_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
+                                           float lambda, int32_t win_length, int32_t n_fft, int32_t hop,
+                                           int32_t n_mels, const dmel_melbank* bank, float log_eps, int32_t flags,
+                                           const float* y, const float* grad_y, float* grad_x, float* grad_lambda,
+                                           void* workspace, size_t workspace_bytes, int32_t prepared,
+                                           void* cuda_stream, const void* peer_bases_dev, int32_t rank,
+                                           int32_t world) {
+    if (!peer_bases_dev) return DMEL_ERR_NULL_POINTER;
+    if (world < 1 || world > PEER_MAX_WORLD || rank < 0 || rank >= world) return DMEL_ERR_BAD_GEOMETRY;
+    return backward_impl(x, batch, n_points, x_row_stride, lambda, win_length, n_fft, hop, n_mels, bank, log_eps, flags, y,
+                         grad_y, grad_x, grad_lambda, workspace, workspace_bytes, prepared, cuda_stream, peer_bases_dev,
+                         rank, world);
 }
 
 extern "C" DMEL_API long long dmel_launch_count(int32_t kind) {
@@ -706,9 +733,8 @@ extern "C" DMEL_API int dmel_peer_allreduce_f32(float* value, const void* peer_b
     if (!value || !peer_bases_dev) return DMEL_ERR_NULL_POINTER;
     if (world < 1 || world > PEER_MAX_WORLD || rank < 0 || rank >= world) return DMEL_ERR_BAD_GEOMETRY;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    // ~0.25 s at 2 GHz: far beyond any healthy skew between ranks, short enough never to look like a hang
-    dmel_peer_allreduce_kernel<<<1, 32, 0, st>>>(value, static_cast<const long long*>(peer_bases_dev), rank, world,
-                                                  500000000LL);
+        dmel_peer_allreduce_kernel<<<1, 32, 0, st>>>(value, static_cast<const long long*>(peer_bases_dev), rank, world,
+                                                  PEER_TIMEOUT_CYCLES);
     return check_launch("dmel_peer_allreduce_kernel");
 }
 

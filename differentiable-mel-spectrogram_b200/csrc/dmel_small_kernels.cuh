@@ -130,12 +130,76 @@ dmel_prep_kernel(const float* __restrict__ x, long long x_stride, int B, int N, 
 }
 
 // ----------------------------------------------------------------------------
+// One-shot all-reduce (sum) of ONE fp32 over NVLink peer memory — the path's only collective (the scalar
+// dL/dlambda).  Every rank owns a symmetric buffer, IPC-mapped into all peers:
+//     float slots[2][world] | int flags[2][world] | int counter | int error
+// Rank r stores its value into slots[parity][r] of EVERY peer, fences, then publishes flags[parity][r] = epoch
+// with a system-scope release; it then acquires its own flags[parity][*] and sums its own slots in rank order,
+// so all ranks obtain the bit-identical total.  `epoch` is a device-side call counter (identical on all ranks, and
+// it keeps advancing under CUDA-graph replay); the parity double-buffering is enough because a peer cannot finish
+// call e+1 before this rank has published call e+1, i.e. after it has read call e.  Spins are bounded: on a
+// timeout the result is NaN and the error word is set (the host falls back to NCCL).
+// ----------------------------------------------------------------------------
+constexpr int PEER_MAX_WORLD = 32;
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// executed by one full warp; returns the total in every lane (NaN + error word on a peer timeout)
+__device__ __forceinline__ float peer_exchange_sum(float v, const long long* __restrict__ peer_bases, int rank, int world,
+                                                   long long timeout_cycles) {
+    const int lane = threadIdx.x & 31;
+    int* mine = reinterpret_cast<int*>(peer_bases[rank]);
+    int epoch = 0;
+    if (lane == 0) epoch = ++mine[4 * world];          // local call counter (only this code touches it)
+    epoch = __shfl_sync(0xffffffffu, epoch, 0);
+    const int parity = epoch & 1;
+    if (lane < world) {
+        int* peer = reinterpret_cast<int*>(peer_bases[lane]);
+        reinterpret_cast<volatile float*>(peer)[parity * world + rank] = v;
+        __threadfence_system();
+        st_release_sys(peer + 2 * world + parity * world + rank, epoch);
+    }
+    float got = 0.f;
+    bool ok = true;
+    if (lane < world) {
+        const int* flag = mine + 2 * world + parity * world + lane;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flag) != epoch) {
+            if (clock64() - t0 > timeout_cycles) { ok = false; break; }
+        }
+        got = reinterpret_cast<volatile float*>(mine)[parity * world + lane];
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    float total = 0.f;
+    for (int r = 0; r < world; ++r) total += __shfl_sync(0xffffffffu, got, r);   // same order on every rank
+    if (!ok) {
+        if (lane == 0) mine[4 * world + 1] = 1;
+        total = __int_as_float(0x7fc00000);
+    }
+    return total;
+}
+
+// ----------------------------------------------------------------------------
 // finalize: dx -= mean(dx) per clip; dL/dlambda -> fp32 with sign(lambda)
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 dmel_finalize_kernel(float* __restrict__ dx, int B, int N, int chunks_per_clip, const double* __restrict__ clipsum,
-                     const WsHeader* hdr, float sign, float* __restrict__ grad_lambda) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *grad_lambda = float(double(sign) * hdr->dlam_acc);
+                     const WsHeader* hdr, float sign, float* __restrict__ grad_lambda,
+                     const long long* __restrict__ peer_bases, int rank, int world, long long timeout_cycles) {
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // local dL/dlambda; with a peer ring the sum over the GPUs happens right here (compute + collective
+        // in one kernel: the other blocks meanwhile apply the mean-removal adjoint to dx)
+        float v = float(double(sign) * hdr->dlam_acc);
+        if (peer_bases != nullptr) v = peer_exchange_sum(v, peer_bases, rank, world, timeout_cycles);
+        if (threadIdx.x == 0) *grad_lambda = v;
+    }
     if (dx == nullptr) return;
     const int b = blockIdx.x / chunks_per_clip;
     const int c = blockIdx.x - b * chunks_per_clip;
@@ -192,61 +256,11 @@ dmel_lambda_grad_kernel(const float* __restrict__ gy, const float* __restrict__ 
     }
 }
 
-// ----------------------------------------------------------------------------
-// One-shot all-reduce (sum) of ONE fp32 over NVLink peer memory — the path's only collective (the scalar
-// dL/dlambda).  Every rank owns a symmetric buffer, IPC-mapped into all peers:
-//     float slots[2][world] | int flags[2][world] | int counter | int error
-// Rank r stores its value into slots[parity][r] of EVERY peer, fences, then publishes flags[parity][r] = epoch
-// with a system-scope release; it then acquires its own flags[parity][*] and sums its own slots in rank order,
-// so all ranks obtain the bit-identical total.  `epoch` is a device-side call counter (identical on all ranks, and
-// it keeps advancing under CUDA-graph replay); the parity double-buffering is enough because a peer cannot finish
-// call e+1 before this rank has published call e+1, i.e. after it has read call e.  Spins are bounded: on a
-// timeout the result is NaN and the error word is set (the host falls back to NCCL).
-// ----------------------------------------------------------------------------
-constexpr int PEER_MAX_WORLD = 32;
-
-__device__ __forceinline__ void st_release_sys(int* p, int v) {
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
-    int v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 __global__ void __launch_bounds__(32)
 dmel_peer_allreduce_kernel(float* __restrict__ value, const long long* __restrict__ peer_bases, int rank, int world,
                            long long timeout_cycles) {
-    const int lane = threadIdx.x;
-    int* mine = reinterpret_cast<int*>(peer_bases[rank]);
-    int epoch = 0;
-    if (lane == 0) epoch = ++mine[4 * world];          // local call counter (only this kernel touches it)
-    epoch = __shfl_sync(0xffffffffu, epoch, 0);
-    const int parity = epoch & 1;
-    const float v = *value;
-    if (lane < world) {
-        int* peer = reinterpret_cast<int*>(peer_bases[lane]);
-        reinterpret_cast<volatile float*>(peer)[parity * world + rank] = v;
-        __threadfence_system();
-        st_release_sys(peer + 2 * world + parity * world + rank, epoch);
-    }
-    float got = 0.f;
-    bool ok = true;
-    if (lane < world) {
-        const int* flag = mine + 2 * world + parity * world + lane;
-        const long long t0 = clock64();
-        while (ld_acquire_sys(flag) != epoch) {
-            if (clock64() - t0 > timeout_cycles) { ok = false; break; }
-        }
-        got = reinterpret_cast<volatile float*>(mine)[parity * world + lane];
-    }
-    ok = __all_sync(0xffffffffu, ok);
-    float total = 0.f;
-    for (int r = 0; r < world; ++r) total += __shfl_sync(0xffffffffu, got, r);   // same order on every rank
-    if (lane == 0) {
-        if (!ok) { mine[4 * world + 1] = 1; total = __int_as_float(0x7fc00000); }
-        *value = total;
-    }
+    const float total = peer_exchange_sum(*value, peer_bases, rank, world, timeout_cycles);
+    if (threadIdx.x == 0) *value = total;
 }
 
 // one launch instead of three memsets: dx (halos are reduced into it), per-clip sums, dL/dlambda accumulator

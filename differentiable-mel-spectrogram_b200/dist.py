@@ -24,17 +24,26 @@ def shard_bounds(n_clips: int, world_size: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def allreduce_lambda_grad(params: Iterable[torch.nn.Parameter], average: bool = False, group=None) -> None:
+def allreduce_lambda_grad(params: Iterable[torch.nn.Parameter], average: bool = False, group=None, ring=None) -> None:
     """SUM (or mean) the .grad of the given lambd parameters over the process group, in place.
 
     Use SUM when each rank back-propagated the gradient of a global (summed) loss through its own
     shard — then the N-rank result equals the 1-rank result on the concatenated batch.
-    All lambdas go out in one flat buffer so there is a single collective per step.
+    All lambdas go out in one flat buffer so there is a single collective per step.  With `ring` (a PeerRing) the
+    exchange is the library's own peer-memory kernel instead of the process group's all_reduce.
     """
     if not dist.is_available() or not dist.is_initialized():
         return
     ps = [p for p in params if p.grad is not None]
     if not ps:
+        return
+    if ring is not None and all(p.grad.dtype == torch.float32 and p.grad.numel() == 1 for p in ps):
+        # one-shot exchange over NVLink peer memory (PeerRing), one 32-thread launch per lambda
+        for p in ps:
+            g = p.grad.detach().view(1)
+            ring.all_reduce_(g)
+            if average:
+                g /= ring.world
         return
     flat = torch.stack([p.grad.detach().reshape(()) for p in ps]) if len(ps) > 1 else ps[0].grad.detach().reshape(1)
     flat = flat.contiguous()

@@ -157,7 +157,7 @@ DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t n_points, 
  * device memory, maps every peer's buffer into its own address space (CUDA IPC) and passes the `world` base
  * pointers (its own at index `rank`) as a DEVICE array of 64-bit addresses.  `value` (device, 1 x fp32) is replaced
  * by the sum, bit-identical on all ranks (summed in rank order).  Stream-ordered, graph-capturable; every rank must
- * make the same sequence of calls.  On a peer timeout (~0.25 s) the result is NaN and word [4*world+1] of the
+ * make the same sequence of calls.  On a peer timeout (~2 s) the result is NaN and word [4*world+1] of the
  * rank's buffer is set to 1.  dist.py (PeerRing) is the host side; NCCL remains the fallback.                     */
 DMEL_API size_t dmel_peer_buffer_bytes(int32_t world);
 /* The symmetric buffers are whole cudaMalloc allocations (that is what a CUDA IPC handle names), owned by the
@@ -171,6 +171,17 @@ DMEL_API int dmel_peer_free(void* buffer);
 DMEL_API int dmel_peer_timed_out(const void* buffer, int32_t world, int32_t* timed_out);
 DMEL_API int dmel_peer_allreduce_f32(float* value, const void* peer_bases_dev, int32_t rank, int32_t world,
                             void* cuda_stream);
+
+/* dmel_backward_f32 with the collective fused in: the finalize kernel that converts the fp64 dL/dlambda sum also
+ * exchanges it with the peers (same protocol as dmel_peer_allreduce_f32, same buffers) while its other blocks apply
+ * the mean-removal adjoint to grad_x; grad_lambda receives the sum over all `world` GPUs.  No separate launch.       */
+DMEL_API int dmel_backward_allreduce_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
+                                float lambda, int32_t win_length, int32_t n_fft, int32_t hop,
+                                int32_t n_mels, const dmel_melbank* bank, float log_eps,
+                                int32_t flags, const float* y, const float* grad_y,
+                                float* grad_x, float* grad_lambda,
+                                void* workspace, size_t workspace_bytes, int32_t prepared,
+                                void* cuda_stream, const void* peer_bases_dev, int32_t rank, int32_t world);
 
 /* Introspection for tests / benchmarks: tile size (frames per CTA), FFT groups per CTA,
  * dynamic shared memory and threads per CTA the launcher would pick.  rows = n_mels or
