@@ -210,6 +210,9 @@ __device__ __forceinline__ void span_centre(float* xs_sh, int p0, int span, int 
 // The dx-producing backward is limited to 4 CTAs per SM by shared memory anyway and runs faster with the full
 // 128 registers (r01e 66 us vs 71 us at 96), so only the forward and the lambda-only backward take the cap.
 __host__ __device__ constexpr int min_ctas(int L, int NG, int NT, bool full_bwd = false) {
+#ifdef DMEL_FULL_BWD_CAP
+    full_bwd = false;   // experiment: cap the dx-producing backward too
+#endif
     return (L <= 512 && NG == 4 && !full_bwd) ? DMEL_MINB_SMALL : (512 / NT > 0 ? 512 / NT : 1);
 }
 

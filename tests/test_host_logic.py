@@ -92,6 +92,17 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_device():
     assert lib.dmel_workspace_bytes(256, 512) >= 64 + 512 * 12 + 256 * 12
 
 
+def test_peer_and_jvp_entry_points_validate_arguments():
+    lib = dm.load()
+    assert lib.dmel_peer_buffer_bytes(8) == (4 * 8 + 4) * 4 and lib.dmel_peer_buffer_bytes(0) == 0 and lib.dmel_peer_buffer_bytes(33) == 0
+    assert lib.dmel_peer_allreduce_f32(None, None, 0, 2, None) == -1
+    assert lib.dmel_peer_allreduce_f32(8, 8, 2, 2, None) == -2          # rank outside the world
+    assert lib.dmel_jvp_supported(512) == 1 and lib.dmel_jvp_supported(16384) == 0 and lib.dmel_jvp_supported(200) == 0
+    assert lib.dmel_lambda_grad_f32(None, None, 10, 1.0, None, None, 0, None) == -1
+    assert lib.dmel_lambda_grad_f32(8, 8, 0, 1.0, 8, 8, 64, None) == -2
+    assert lib.dmel_workspace_y_sum_offset() % 8 == 0 and lib.dmel_workspace_y_sum_offset() < 64
+
+
 def test_launch_plans_fit_shared_memory():
     for (B, N, L, hop, rows) in [(256, 8000, 512, 80, 64), (128, 220500, 2048, 441, 128), (1024, 160000, 1024, 160, 128),
                                  (512, 8000, 4096, 80, 64), (512, 8000, 128, 80, 64), (64, 256, 512, 1, 0), (128, 128, 256, 1, 0),
