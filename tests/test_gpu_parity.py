@@ -245,6 +245,26 @@ def test_strided_rows_fp16_input_and_negative_lambda(cuda_device):
     check_y(yh.detach().cpu().numpy(), w.numpy(), True)
 
 
+@pytest.mark.parametrize("offset,N", [(1, 1600), (2, 1603), (3, 4001), (101, 1599)])
+def test_unaligned_input_rows_take_the_scalar_copy_path(cuda_device, offset, N):
+    """x rows that are only 4-byte aligned (a column slice of a bigger buffer): the 16-byte async copies must not be used."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(offset + N)
+    big = torch.randn(3, N + 2 * offset + 5, generator=g)
+    x = big[:, offset:offset + N]
+    T = N // 80 + 1
+    G = torch.randn(3, 1, 32, T, generator=g)
+    kw_o = dict(hop=80, optimized=True, n_mels=32, sample_rate=8000)
+    want = orc.port_forward_backward(x.contiguous(), 46.667, G, use_log=True, batched=True, **kw_o)
+    xs = big.to(dev)[:, offset:offset + N].requires_grad_(True)
+    assert xs.data_ptr() % 16 != 0 or xs.stride(0) % 4 != 0
+    ll = torch.tensor(46.667, device=dev, requires_grad=True)
+    y = dm.dmel(xs, ll, hop_length=80, optimized=True, n_mels=32, sample_rate=8000, log_eps=EPS)
+    (y * G.to(dev)).sum().backward()
+    check_y(y.detach().cpu().numpy(), want[0], False)
+    check_grads(xs.grad.cpu().numpy(), float(ll.grad), want[1], want[2])
+
+
 def test_all_zero_input_hits_the_log_floor_exactly(cuda_device):
     layer = dm.MelSpectrogramLayer(torch.tensor(46.667), n_mels=64, n_points=1600, sample_rate=8000, hop_length=80,
                                    device="cuda:0", optimized=True, log_eps=EPS).to(cuda_device)
