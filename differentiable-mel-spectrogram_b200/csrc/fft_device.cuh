@@ -143,6 +143,11 @@ template <int ROT> __device__ __forceinline__ int swz(int i) {
 __host__ __device__ constexpr int swz_rot(int NS, int R) {
     return NS >= 16 ? 0 : ((NS * R >= 16) ? (16 / R) : NS);
 }
+// compile-time swizzle of a constant offset.  For every plan below, swz(base + r*stride) == swz(base) ^ swz(r*stride)
+// (the bit fields of base and r*stride never overlap; checked exhaustively by tests/test_host_logic.py), so a
+// butterfly computes the swizzle of its base index once and reaches its R elements with one XOR (ROT != 0) or a
+// plain immediate offset (ROT == 0) each.
+__host__ __device__ constexpr int swz_const(int rot, int i) { return rot ? (i ^ ((rot * (i >> 4)) & 15)) : i; }
 
 // barrier over the GT threads of one group (bar_id in 1..15 is private to the group)
 template <int GT> __device__ __forceinline__ void group_sync(int bar_id) {
@@ -174,9 +179,12 @@ template <int L, int P> struct Pass {
     static __device__ __forceinline__ void gather(float2 (&v)[E], const float2* __restrict__ in, int gtid) {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            const int j = gtid + i * GT;
+            const int base = swz<ROT_IN>(gtid + i * GT);
 #pragma unroll
-            for (int r = 0; r < R; ++r) v[i * R + r] = in[swz<ROT_IN>(j + r * STR)];
+            for (int r = 0; r < R; ++r) {
+                if (ROT_IN == 0) v[i * R + r] = in[base + r * STR];
+                else v[i * R + r] = in[base ^ swz_const(ROT_IN, r * STR)];
+            }
         }
     }
 
@@ -204,9 +212,12 @@ template <int L, int P> struct Pass {
         for (int i = 0; i < NB; ++i) {
             const int j = gtid + i * GT;
             const int k = j & (NS - 1);
-            const int j0 = (j - k) * R + k;
+            const int base = swz<ROT_OUT>((j - k) * R + k);
 #pragma unroll
-            for (int r = 0; r < R; ++r) out[swz<ROT_OUT>(j0 + r * NS)] = v[i * R + r];
+            for (int r = 0; r < R; ++r) {
+                if (ROT_OUT == 0) out[base + r * NS] = v[i * R + r];
+                else out[base ^ swz_const(ROT_OUT, r * NS)] = v[i * R + r];
+            }
         }
     }
 

@@ -92,6 +92,34 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_device():
     assert lib.dmel_workspace_bytes(256, 512) >= 64 + 512 * 12 + 256 * 12
 
 
+def test_fft_plan_swizzle_is_xor_separable():
+    """fft_device.cuh reaches the R elements of a butterfly as swz(base) ^ swz(r*stride): that needs
+    swz(base + r*stride) == swz(base) ^ swz(r*stride) for every plan, pass, thread and r."""
+    plans = {128: (4, [4, 4, 4, 2]), 256: (8, [8, 8, 4]), 512: (16, [8, 8, 8]), 1024: (16, [16, 8, 8]), 2048: (16, [16, 16, 8]),
+             4096: (16, [16, 16, 16]), 8192: (32, [16, 16, 8, 4]), 16384: (32, [16, 16, 8, 8])}
+    rot = lambda NS, R: 0 if NS >= 16 else (16 // R if NS * R >= 16 else NS)          # noqa: E731
+    swz = lambda i, ro: i ^ ((ro * (i >> 4)) & 15) if ro else i                        # noqa: E731
+    for L, (E, rad) in plans.items():
+        GT, NS = L // E, 1
+        assert int(np.prod(rad)) == L
+        for p, R in enumerate(rad):
+            ro_out = rot(NS, R)
+            ro_in = 0 if p == 0 else rot(NS // rad[p - 1], rad[p - 1])
+            STR = L // R
+            seen = set()
+            for tid in range(GT):
+                for i in range(E // R):
+                    j = tid + i * GT
+                    k = j & (NS - 1)
+                    j0 = (j - k) * R + k
+                    for r in range(R):
+                        assert swz(j0 + r * NS, ro_out) == swz(j0, ro_out) ^ swz(r * NS, ro_out)
+                        assert swz(j + r * STR, ro_in) == swz(j, ro_in) ^ swz(r * STR, ro_in)
+                        seen.add(swz(j0 + r * NS, ro_out))
+            assert seen == set(range(L))               # the scatter is a permutation of the buffer
+            NS *= R
+
+
 def test_peer_and_jvp_entry_points_validate_arguments():
     lib = dm.load()
     assert lib.dmel_peer_buffer_bytes(8) == (4 * 8 + 4) * 4 and lib.dmel_peer_buffer_bytes(0) == 0 and lib.dmel_peer_buffer_bytes(33) == 0
