@@ -31,6 +31,9 @@ class _LambdaMirror:
         self._key = None
         self._value = 0.0
 
+    def invalidate(self) -> None:
+        self._key = None
+
     def get(self, lambd: torch.Tensor) -> float:
         key = (lambd._version, lambd.data_ptr(), lambd.device)
         if key != self._key:
@@ -86,6 +89,12 @@ class MelSpectrogramLayer(nn.Module):
                                    log_eps=self.log_eps, lambd_value=self._mirror.get(self.lambd), return_energy=True)
         return y
 
+    def invalidate_lambda_cache(self) -> None:
+        """Force the next forward to re-read `lambd` from the device.  Only needed after writes that bypass
+        autograd's version counter (`layer.lambd.data.add_(...)`-style code); optimizers, `fill_`, `copy_` and
+        `load_state_dict` are picked up automatically."""
+        self._mirror.invalidate()
+
     def extra_repr(self):
         return (f"n_mels={self.n_mels}, sample_rate={self.sample_rate}, hop_length={self.hop_length}, "
                 f"optimized={self.optimized}, normalize_window={self.normalize_window}, log_eps={self.log_eps}")
@@ -120,6 +129,10 @@ class SpectrogramLayer(nn.Module):
             # models.py:186,198: the reference allocates `size` and assigns the (F, T) spectrogram into it
             raise RuntimeError(f"spectrogram of shape {tuple(s.shape[2:])} does not fit size={tuple(self.size)}")
         return s
+
+    def invalidate_lambda_cache(self) -> None:
+        """See MelSpectrogramLayer.invalidate_lambda_cache."""
+        self._mirror.invalidate()
 
     def extra_repr(self):
         return (f"hop_length={self.hop_length}, optimized={self.optimized}, size={self.size}, "

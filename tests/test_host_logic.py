@@ -166,6 +166,21 @@ def test_layers_keep_the_reference_contract_and_refuse_cpu():
         dm.dmel(torch.zeros(2, 128), torch.tensor(6.38), hop_length=1, optimized=False)
 
 
+def test_lambda_mirror_follows_parameter_writes():
+    layer = dm.MelSpectrogramLayer(torch.tensor(46.667), n_mels=64, n_points=8000, sample_rate=8000, hop_length=80)
+    m = layer._mirror
+    assert abs(m.get(layer.lambd) - 46.667) < 1e-4
+    opt = torch.optim.SGD([layer.lambd], lr=1.0)
+    layer.lambd.grad = torch.tensor(2.0)
+    opt.step()                                           # in-place update under no_grad bumps the version counter
+    assert abs(m.get(layer.lambd) - 44.667) < 1e-4
+    layer.load_state_dict({"lambd": torch.tensor(90.0)})
+    assert m.get(layer.lambd) == 90.0
+    layer.lambd.data.fill_(13.0)                         # bypasses the version counter ...
+    layer.invalidate_lambda_cache()                      # ... so the documented escape hatch is needed
+    assert m.get(layer.lambd) == 13.0
+
+
 def test_product_package_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "differentiable-mel-spectrogram_b200")
     for fn in os.listdir(pkg):
