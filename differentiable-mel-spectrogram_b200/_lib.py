@@ -16,6 +16,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 ABI_VERSION = 1
 FLAG_NORMALIZE_WINDOW = 1
 FLAG_KEEP_MEAN = 2
+FLAG_TIME_MAJOR = 4
 
 # every symbol include/dmel.h declares
 EXPORTED_SYMBOLS = (

@@ -68,6 +68,7 @@ struct Geom {
     float log_eps;
     int row_aligned;             // x and x_stride are 16-byte aligned: spans may move as 16-byte quads
     int lookahead;               // 1: span (and dL/dy, y) buffers are doubled and tile i+1 is prefetched during tile i
+    int time_major;              // y / dL/dy / dy are (B,1,T,rows) instead of (B,1,rows,T)
 };
 
 struct MelDev {

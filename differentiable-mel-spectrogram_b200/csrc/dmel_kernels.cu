@@ -518,6 +518,7 @@ static Geom make_geom(int64_t B, int64_t N, int64_t stride, int32_t n_fft, int32
     g.log_eps = log_eps;
     g.row_aligned = 0;
     g.lookahead = lp.lookahead;
+    g.time_major = 0;
     return g;
 }
 
@@ -536,12 +537,14 @@ static int forward_impl(const float* x, int64_t batch, int64_t n_points, int64_t
                           false, &lp, dy != nullptr)))
         return rc;
     if (dy && lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;   // the JVP forward exists for the tiled FFT path only
+    if ((flags & DMEL_FLAG_TIME_MAJOR) && lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;   // likewise the (B,1,T,M) layout
     if (int64_t(batch) * lp.tiles_per_clip > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
     WsView ws = ws_view(workspace, batch, n_fft);
     if ((rc = run_prep(x, batch, n_points, x_row_stride, fabsf(lambda), win_length, n_fft, flags, ws, st)))
         return rc;
     Geom g = make_geom(batch, n_points, x_row_stride, n_fft, hop, rows, log_eps, lp);
     g.row_aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_row_stride & 3) == 0) ? 1 : 0;
+    g.time_major = (flags & DMEL_FLAG_TIME_MAJOR) ? 1 : 0;
     const MelDev mel = mel_dev(bank);
     if (lp.path == 1) {
         if ((rc = set_smem(dmel_dft_kernel<false, false>, lp.smem))) return rc;
@@ -628,6 +631,8 @@ static int backward_impl(const float* x, int64_t batch, int64_t n_points, int64_
     }
     Geom g = make_geom(batch, n_points, x_row_stride, n_fft, hop, rows, log_eps, lp);
     g.row_aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_row_stride & 3) == 0) ? 1 : 0;
+    g.time_major = (flags & DMEL_FLAG_TIME_MAJOR) ? 1 : 0;
+    if (g.time_major && lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;
     const MelDev mel = mel_dev(bank);
     if (lp.path == 1) {
         const unsigned grid = unsigned(int64_t(g.B) * g.T);

@@ -159,22 +159,29 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __res
         }
         __syncthreads();
         // models.py:54 pack into (B,1,M,T), T fastest; optional fused log (models.py:72-73)
-        float* yb = y + (long long)b * g.M * g.T + t0;
-        float* dyb = JVP ? dy + (long long)b * g.M * g.T + t0 : nullptr;
-        for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
-            const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
-            if (tt < nfr) {
-                float val = tile[m * TS + tt];
-                if (JVP) {
-                    // d log(mel + eps) / d|lambda| = dmel / (mel + eps)
-                    const float dv = tile2[m * TS + tt];
-                    dyb[(long long)m * g.T + tt] = do_log ? __fdividef(dv, val + g.log_eps) : dv;
-                }
-                // lg2.approx * ln2: <= 3 ulp, i.e. ~1e-6 absolute on log-mel values (budget 1e-5 + 1e-4 |y|)
-                if (do_log) val = __logf(val + g.log_eps);
-                yb[(long long)m * g.T + tt] = val;
-                ysum += val;
+        // (with g.time_major the result is (B,1,T,M), M fastest: what MelPANNsNet transposes to, models.py:162)
+        auto emit = [&](int m, int tt, long long off) {
+            float val = tile[m * TS + tt];
+            if (JVP) {
+                // d log(mel + eps) / d|lambda| = dmel / (mel + eps)
+                const float dv = tile2[m * TS + tt];
+                dy[off] = do_log ? __fdividef(dv, val + g.log_eps) : dv;
             }
+            // lg2.approx * ln2: <= 3 ulp, i.e. ~1e-6 absolute on log-mel values (budget 1e-5 + 1e-4 |y|)
+            if (do_log) val = __logf(val + g.log_eps);
+            y[off] = val;
+            ysum += val;
+        };
+        if (!g.time_major) {
+            const long long base = (long long)b * g.M * g.T + t0;
+            for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
+                const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
+                if (tt < nfr) emit(m, tt, base + (long long)m * g.T + tt);
+            }
+        } else {
+            const long long base = ((long long)b * g.T + t0) * g.M;
+            for (int tt = tid >> 5; tt < nfr; tt += NT / 32)
+                for (int m = tid & 31; m < g.M; m += 32) emit(m, tt, base + (long long)tt * g.M + m);
         }
         // the next iteration's staging only writes xs; its __syncthreads orders it after this epilogue
     }
@@ -245,13 +252,26 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
         // are 4-byte async ones, all in flight together; columns past the last frame are zero
         float* gt_ = gt + slot * 2 * tile_words;
         float* yt_ = gt_ + tile_words;
-        const long long base = (long long)b_ * g.M * g.T + t0_;
-        for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
-            const int m = idx >> tt_shift, tt = idx & (g.TT - 1);   // consecutive lanes: consecutive frames
-            const bool ok = tt < nfr_;
-            const long long off = base + (long long)m * g.T + (ok ? tt : 0);
-            cp_async4_zfill(gt_ + m * TS + tt, gy + off, ok);
-            if (do_log) cp_async4_zfill(yt_ + m * TS + tt, y + off, ok);
+        if (!g.time_major) {
+            const long long base = (long long)b_ * g.M * g.T + t0_;
+            for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
+                const int m = idx >> tt_shift, tt = idx & (g.TT - 1);   // consecutive lanes: consecutive frames
+                const bool ok = tt < nfr_;
+                const long long off = base + (long long)m * g.T + (ok ? tt : 0);
+                cp_async4_zfill(gt_ + m * TS + tt, gy + off, ok);
+                if (do_log) cp_async4_zfill(yt_ + m * TS + tt, y + off, ok);
+            }
+        } else {
+            // (B,1,T,M) layout: consecutive lanes read consecutive mel bins of one frame
+            const long long base = ((long long)b_ * g.T + t0_) * g.M;
+            for (int tt = tid >> 5; tt < g.TT; tt += NT / 32) {
+                const bool ok = tt < nfr_;
+                for (int m = tid & 31; m < g.M; m += 32) {
+                    const long long off = base + (long long)(ok ? tt : 0) * g.M + m;
+                    cp_async4_zfill(gt_ + m * TS + tt, gy + off, ok);
+                    if (do_log) cp_async4_zfill(yt_ + m * TS + tt, y + off, ok);
+                }
+            }
         }
     };
     const bool ahead = g.lookahead != 0;
@@ -277,9 +297,14 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
         span_centre<NT>(xs_cur, p0, g.span, g.N, mu, tid);
         if (do_log) {
             // dL/dmel = G / (mel + eps) = G * exp(-y); each thread touches the words it copied itself
-            for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
-                const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
-                gtc[m * TS + tt] *= __expf(-ytc[m * TS + tt]);
+            if (!g.time_major) {
+                for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
+                    const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
+                    gtc[m * TS + tt] *= __expf(-ytc[m * TS + tt]);
+                }
+            } else {
+                for (int tt = tid >> 5; tt < g.TT; tt += NT / 32)
+                    for (int m = tid & 31; m < g.M; m += 32) gtc[m * TS + tt] *= __expf(-ytc[m * TS + tt]);
             }
         }
         __syncthreads();   // also: every warp is done with the previous tile

@@ -50,7 +50,7 @@ def _resolve_device(module_device, lambd: torch.Tensor) -> torch.device:
 
 class MelSpectrogramLayer(nn.Module):
     def __init__(self, init_lambd, n_mels, n_points, sample_rate, f_min=0, f_max=None, hop_length=1, device='cpu',
-                 optimized=False, normalize_window=False, *, log_eps: Optional[float] = None):
+                 optimized=False, normalize_window=False, *, log_eps: Optional[float] = None, time_major: bool = False):
         super().__init__()
         self.hop_length = hop_length
         self.lambd = nn.Parameter(init_lambd)
@@ -66,6 +66,7 @@ class MelSpectrogramLayer(nn.Module):
         self.n_freq = n_mels
         self.n_time = n_points // hop_length + 1
         self.log_eps = log_eps
+        self.time_major = time_major      # True: (B, 1, n_time, n_mels), what MelPANNsNet feeds Cnn6 (models.py:162)
         self._mirror = _LambdaMirror()
         # 0-d fp64 device tensor: sum of the last forward's output, produced inside the kernel (train.py:58)
         self.last_energy = None
@@ -86,7 +87,8 @@ class MelSpectrogramLayer(nn.Module):
         y, self.last_energy = dmel(x, self.lambd, hop_length=self.hop_length, optimized=self.optimized,
                                    normalize_window=self.normalize_window, n_mels=self.n_mels,
                                    sample_rate=self.sample_rate, f_min=self.f_min, f_max=self.f_max,
-                                   log_eps=self.log_eps, lambd_value=self._mirror.get(self.lambd), return_energy=True)
+                                   log_eps=self.log_eps, lambd_value=self._mirror.get(self.lambd), return_energy=True,
+                                   time_major=self.time_major)
         return y
 
     def invalidate_lambda_cache(self) -> None:

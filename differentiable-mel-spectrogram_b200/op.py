@@ -113,7 +113,8 @@ class DmelFunction(torch.autograd.Function):
                 log_eps: float, flags: int, lam_value: float):
         lib = _lib.load()
         dev = x.device
-        y = torch.empty((geo.batch, 1, geo.rows, geo.n_frames), dtype=torch.float32, device=dev)
+        shape = (geo.batch, 1, geo.n_frames, geo.rows) if (flags & _lib.FLAG_TIME_MAJOR) else (geo.batch, 1, geo.rows, geo.n_frames)
+        y = torch.empty(shape, dtype=torch.float32, device=dev)
         wkey = (geo.batch, geo.n_fft)
         ws_bytes = _ws_bytes_cache.get(wkey)
         if ws_bytes is None:
@@ -195,7 +196,7 @@ class DmelFunction(torch.autograd.Function):
 def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bool,
          normalize_window: bool = False, n_mels: int = 0, sample_rate: int = 0, f_min: float = 0.0,
          f_max: Optional[float] = None, log_eps: Optional[float] = None, remove_mean: bool = True,
-         lambd_value: Optional[float] = None, return_energy: bool = False):
+         lambd_value: Optional[float] = None, return_energy: bool = False, time_major: bool = False):
     """Functional form of both layers.
 
     x: (B, N) CUDA tensor (fp32; fp64/fp16 inputs are cast to fp32 — the reference's fp64
@@ -205,7 +206,8 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
     n_mels == 0 selects spectrogram mode (models.py:171-200).  `lambd_value`, if given, must equal
     lambd's current value (it only saves the device->host read that picks n_fft).  With `return_energy`
     the result is `(y, energy)`, energy a 0-d fp64 device tensor = y.sum() computed inside the forward kernel
-    (what train.py:58 copies the whole spectrogram batch to the host for).
+    (what train.py:58 copies the whole spectrogram batch to the host for).  `time_major=True` returns
+    (B, 1, N//hop + 1, rows) instead — the layout MelPANNsNet transposes to before Cnn6 (models.py:162).
     """
     if x.dim() != 2:
         raise ValueError(f"expected x of shape (batch, n_points), got {tuple(x.shape)}")
@@ -226,7 +228,7 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
         raise ValueError("log_eps must be >= 0")
     # everything below depends only on these scalars: resolve once, reuse while they repeat (training loops)
     key = (B, N, hop_length, lam_value, optimized, normalize_window, n_mels, sample_rate, f_min, f_max, log_eps, remove_mean,
-           x.device.index)
+           time_major, x.device.index)
     plan = _plan_cache.get(key)
     if plan is None:
         geo = resolve_geometry(B, N, hop_length, lam_value, optimized, n_mels)
@@ -237,7 +239,10 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
         if n_mels > 0:
             fmax = f_max if f_max is not None else sample_rate // 2
             bank = device_bank(geo.n_freqs, f_min, fmax, n_mels, sample_rate, x.device)
-        flags = (_lib.FLAG_NORMALIZE_WINDOW if normalize_window else 0) | (0 if remove_mean else _lib.FLAG_KEEP_MEAN)
+        flags = ((_lib.FLAG_NORMALIZE_WINDOW if normalize_window else 0) | (0 if remove_mean else _lib.FLAG_KEEP_MEAN)
+                 | (_lib.FLAG_TIME_MAJOR if time_major else 0))
+        if time_major and not lib.dmel_jvp_supported(geo.n_fft):
+            raise _lib.DmelError(f"time_major output is implemented for n_fft 128..4096, got {geo.n_fft}")
         eps = -1.0 if log_eps is None else float(log_eps)
         plan = (geo, bank, eps, flags)
         if len(_plan_cache) > 64:

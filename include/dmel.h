@@ -39,6 +39,7 @@ extern "C" {
 
 #define DMEL_FLAG_NORMALIZE_WINDOW 1
 #define DMEL_FLAG_KEEP_MEAN 2
+#define DMEL_FLAG_TIME_MAJOR 4   /* y, grad_y, dy_dlambda are [batch,1,T,rows] (rows fastest) instead of [batch,1,rows,T] */
 
 typedef enum dmel_status {
     DMEL_OK = 0,
@@ -108,7 +109,9 @@ DMEL_API size_t dmel_workspace_y_sum_offset(void);
  *   log_eps     >= 0: y = log(mel + log_eps) fused (models.py:72-73); < 0: linear
  *   flags       DMEL_FLAG_NORMALIZE_WINDOW: time_frequency.py:25-30 `norm`;
  *               DMEL_FLAG_KEEP_MEAN: skip the per-clip mean removal of models.py:38 (what a
- *               direct caller of time_frequency.differentiable_spectrogram gets)
+ *               direct caller of time_frequency.differentiable_spectrogram gets);
+ *               DMEL_FLAG_TIME_MAJOR: emit [batch,1,T,rows] — the layout MelPANNsNet transposes to
+ *               before Cnn6 (models.py:162) — tiled FFT path only (n_fft 128..4096)
  *   y           [batch, 1, rows, T] fp32 contiguous, rows = n_mels or n_fft/2+1
  *   workspace   >= dmel_workspace_bytes(batch, n_fft); filled here (means, window,
  *               twiddles) and reusable by dmel_backward_f32 with prepared = 1      */

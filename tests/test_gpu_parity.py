@@ -343,6 +343,33 @@ def test_drop_in_module_contract(cuda_device):
     assert net(x)[1].shape == (8, 1, 64, 101)
 
 
+@pytest.mark.parametrize("lam,M,sr,hop,N", [(46.667, 64, 8000, 80, 8000), (93.33, 128, 16000, 160, 16000), (257.25, 128, 44100, 441, 22050)])
+def test_time_major_layout_is_the_exact_transpose(cuda_device, lam, M, sr, hop, N):
+    """MelPANNsNet transposes the layer output to (B,1,T,M) (models.py:162); the kernels can emit it."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(int(lam))
+    x = torch.randn(6, N, generator=g).to(dev)
+    T = N // hop + 1
+    G = torch.randn(6, 1, M, T, generator=g).to(dev)
+    kw = dict(hop_length=hop, optimized=True, n_mels=M, sample_rate=sr, log_eps=EPS)
+    for need_dx in (True, False):                      # recomputing backward / forward-mode (JVP) path
+        res = []
+        for tm in (False, True):
+            xin = x.clone().requires_grad_(need_dx)
+            ll = torch.tensor(lam, device=dev, requires_grad=True)
+            y = dm.dmel(xin, ll, time_major=tm, **kw)
+            assert y.is_contiguous() and y.shape == ((6, 1, T, M) if tm else (6, 1, M, T))
+            (y * (G.transpose(2, 3) if tm else G)).sum().backward()
+            res.append((y.detach(), xin.grad, float(ll.grad)))
+        assert torch.equal(res[1][0], res[0][0].transpose(2, 3))
+        if need_dx:
+            assert rel_err(res[1][1].cpu().numpy(), res[0][1].cpu().numpy()) < 1e-6
+        assert abs(res[1][2] - res[0][2]) <= 1e-6 * abs(res[0][2])
+    layer = dm.MelSpectrogramLayer(torch.tensor(lam), n_mels=M, n_points=N, sample_rate=sr, hop_length=hop, device="cuda:0",
+                                   optimized=True, log_eps=EPS, time_major=True).to(dev)
+    assert layer(x).shape == (6, 1, T, M)
+
+
 def test_fused_energy_sum_equals_output_sum(cuda_device):
     """train.py:58 copies every spectrogram batch to the host to add it up; the kernel leaves the sum."""
     dev = cuda_device
