@@ -71,21 +71,35 @@ _lock = threading.Lock()
 _lib = None
 
 
+def _source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith((".cu", ".cuh")) or f == "Makefile")
+    files.append(os.path.join(_HERE, "..", "include", "dmel.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/ for sm_100a into libdmel_b200.so (in-tree) with nvcc."""
-    srcs = [os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith((".cu", ".cuh")) or f == "Makefile"]
-    srcs.append(os.path.join(_HERE, "..", "include", "dmel.h"))
-    if not force and os.path.exists(LIB_PATH):
-        newest = max(os.path.getmtime(s) for s in srcs if os.path.exists(s))
-        if os.path.getmtime(LIB_PATH) >= newest:
-            return LIB_PATH
-    cmd = ["make", "-C", CSRC_DIR] + (["-B"] if force else [])
-    proc = subprocess.run(cmd, capture_output=True, text=True)
+    """Compile csrc/ for sm_100a into libdmel_b200.so (in-tree) with nvcc.  Up-to-date-ness is decided by a hash of
+    the sources stored next to the library (file times do not survive the copy to the GPU box)."""
+    stamp = LIB_PATH + ".srchash"
+    want = _source_hash()
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
+        with open(stamp) as fh:
+            if fh.read().strip() == want:
+                return LIB_PATH
+    proc = subprocess.run(["make", "-B", "-C", CSRC_DIR], capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         print(proc.stdout)
         print(proc.stderr)
     if proc.returncode != 0:
         raise DmelError(f"building libdmel_b200.so failed (exit {proc.returncode})")
+    with open(stamp, "w") as fh:
+        fh.write(want + "\n")
     return LIB_PATH
 
 
