@@ -5,7 +5,8 @@
 // complex transform); a CTA runs several such groups independently.  Each thread keeps
 // E complex points in registers; a Stockham pass is
 //   load (stride L/R)  ->  twiddle  ->  radix-R DFT in registers  ->  scatter (stride NS)
-// with the scatter/gather going through a ping-pong pair of shared-memory buffers.
+// with the scatter/gather going through ONE shared-memory buffer per group (a group barrier on each side of a
+// scatter; for one-warp groups that is __syncwarp).
 // The shared-memory index is XOR-swizzled per pass so that both the strided scatter
 // of the early passes and the contiguous gather of the next pass are conflict-free
 // for 64-bit accesses (16 lanes x 8 B per wavefront).

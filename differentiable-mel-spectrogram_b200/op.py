@@ -105,8 +105,14 @@ _Y_SUM_OFFSET = [-1]
 
 
 class DmelFunction(torch.autograd.Function):
-    """y = DMEL(x, lambd); saves only x, lambd (and y when the log is fused) plus the small
-    workspace (per-clip means, window, twiddles) — spectra are recomputed in backward."""
+    """y = DMEL(x, lambd).
+
+    Two regimes, chosen from `needs_input_grad` at forward time:
+      * x needs a gradient  -> forward saves only x (and y when the log is fused) plus the small workspace (per-clip
+        means, window, twiddles); the backward kernel recomputes the spectra and produces dL/dx and dL/dlambd;
+      * only lambd does (the reference's training case) -> the forward-mode kernel also writes dy/dlambd, which is
+        saved instead of x; the backward is a dot product with dL/dy.
+    """
 
     @staticmethod
     def forward(ctx, x: torch.Tensor, lambd: torch.Tensor, geo: Geometry, bank: Optional[DeviceBank],
