@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmel_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
-ABI_VERSION = 1
+ABI_VERSION = 2
 FLAG_NORMALIZE_WINDOW = 1
 FLAG_KEEP_MEAN = 2
 FLAG_TIME_MAJOR = 4
@@ -60,6 +60,8 @@ class MelBankStruct(ctypes.Structure):
         ("bin_m0", ctypes.c_void_p),
         ("bin_off", ctypes.c_void_p),
         ("bin_w", ctypes.c_void_p),
+        ("out_scale", ctypes.c_void_p),
+        ("out_shift", ctypes.c_void_p),
     ]
 
 

@@ -121,6 +121,7 @@ dmel_big_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, 
             if (tt < nfr) {
                 float val = tile[m * TS + tt];
                 if (do_log) val = __logf(val + g.log_eps);
+                if (mel.out_scale) val = affine_out(mel, m, val);
                 yb[(long long)m * g.T + tt] = val;
                 ysum += val;
             }
@@ -172,7 +173,8 @@ dmel_big_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, co
             if (tt < nfr) {
                 const long long off = ybase + (long long)m * g.T + tt;
                 val = __ldg(gy + off);
-                if (do_log) val *= __expf(-__ldg(y + off));
+                if (mel.out_scale) val *= affine_grad_factor(mel, m, do_log ? __ldg(y + off) : 0.f, do_log);
+                else if (do_log) val *= __expf(-__ldg(y + off));
             }
             gt[m * TS + tt] = val;
         }

@@ -78,7 +78,24 @@ struct MelDev {
     const int* bin_m0;
     const int* bin_off;
     const float* bin_w;
+    const float* out_scale;   // per-mel affine folded into the epilogue (dmel.h); both null = identity
+    const float* out_shift;
 };
+
+template <bool V> struct BoolTag { static constexpr bool value = V; };
+
+// forward epilogue: y <- scale[m]*y + shift[m]
+__device__ __forceinline__ float affine_out(const MelDev& mel, int m, float v) {
+    return fmaf(v, __ldg(mel.out_scale + m), __ldg(mel.out_shift + m));
+}
+// backward: factor that turns dL/dy' (y' the mapped output) into dL/dmel.  With the log fused,
+// log-mel = (y' - shift)/scale and dL/dmel = G * scale * exp(-log-mel); scale == 0 gives 0.
+__device__ __forceinline__ float affine_grad_factor(const MelDev& mel, int m, float y_out, bool do_log) {
+    const float a = __ldg(mel.out_scale + m);
+    if (!do_log) return a;
+    const float ia = a != 0.f ? 1.f / a : 0.f;
+    return a * __expf(-(y_out - __ldg(mel.out_shift + m)) * ia);
+}
 
 // ----------------------------------------------------------------------------
 // block reductions

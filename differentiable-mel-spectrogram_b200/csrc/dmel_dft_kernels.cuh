@@ -63,6 +63,7 @@ dmel_dft_kernel(const float* __restrict__ x, const float* __restrict__ y_in, con
                 for (int o = o0; o < o1; ++o) s = fmaf(__ldg(mel.mel_w + o), gp[k0 + (o - o0)], s);
             }
             if (do_log) s = logf(s + g.log_eps);
+            if (!spec_mode && mel.out_scale) s = affine_out(mel, m, s);
             yb[(long long)m * g.T] = s;
             ysum_dft += s;
         }
@@ -83,7 +84,8 @@ dmel_dft_kernel(const float* __restrict__ x, const float* __restrict__ y_in, con
             for (int o = o0; o < o1; ++o) {
                 const long long off = ybase + (long long)(m0 + (o - o0)) * g.T;
                 float gv = __ldg(gy + off);
-                if (do_log) gv *= expf(-__ldg(y_in + off));
+                if (mel.out_scale) gv *= affine_grad_factor(mel, m0 + (o - o0), do_log ? __ldg(y_in + off) : 0.f, do_log);
+                else if (do_log) gv *= expf(-__ldg(y_in + off));
                 ga = fmaf(__ldg(mel.bin_w + o), gv, ga);
             }
         }

@@ -412,6 +412,7 @@ static int validate(const float* x, int64_t B, int64_t N, int64_t stride, int32_
                              reinterpret_cast<uintptr_t>(bank->mel_w) | reinterpret_cast<uintptr_t>(bank->bin_m0) |
                              reinterpret_cast<uintptr_t>(bank->bin_off) | reinterpret_cast<uintptr_t>(bank->bin_w);
         if (al & 15) return DMEL_ERR_BAD_MELBANK;  // the arrays are staged with 16-byte async copies
+        if ((bank->out_scale == nullptr) != (bank->out_shift == nullptr)) return DMEL_ERR_BAD_MELBANK;
     }
     if (ws_bytes_in < ws_bytes(B, n_fft)) return DMEL_ERR_WORKSPACE_TOO_SMALL;
     return DMEL_OK;
@@ -422,6 +423,7 @@ static MelDev mel_dev(const dmel_melbank* bank) {
     if (bank) {
         m.mel_k0 = bank->mel_k0; m.mel_off = bank->mel_off; m.mel_w = bank->mel_w;
         m.bin_m0 = bank->bin_m0; m.bin_off = bank->bin_off; m.bin_w = bank->bin_w;
+        m.out_scale = bank->out_scale; m.out_shift = bank->out_shift;
     }
     return m;
 }
@@ -429,8 +431,20 @@ static MelDev mel_dev(const dmel_melbank* bank) {
 static int run_prep(const float* x, int64_t B, int64_t N, int64_t stride, float lam_abs, int32_t win, int32_t n_fft,
                     int32_t flags, const WsView& ws, cudaStream_t st) {
     ProfScope prof(PROF_PREP, st);
-    dmel_prep_kernel<<<unsigned(B + 1), PREP_THREADS, 0, st>>>(x, stride, int(B), int(N), lam_abs, win, n_fft,
-                                                                flags, ws, fft_info(n_fft).desc);
+    const int nseg = prep_segments(int(N));
+    if ((B + 1) * int64_t(nseg) > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned((B + 1) * nseg));
+    cfg.blockDim = dim3(PREP_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = unsigned(nseg);
+    attr.val.clusterDim.y = attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, dmel_prep_kernel, x, (long long)stride, int(B), int(N), lam_abs, int(win), int(n_fft),
+                       int(flags), ws, fft_info(n_fft).desc);
     return check_launch("dmel_prep_kernel");
 }
 

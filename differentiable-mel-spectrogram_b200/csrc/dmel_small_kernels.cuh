@@ -1,9 +1,12 @@
 // dmel_small_kernels.cuh — prep (means, window, twiddles), zero-init and finalize kernels
 // Part of libdmel_b200.so (single translation unit, see dmel_kernels.cu for the overview).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "dmel_common.cuh"
 
 namespace dmel {
+namespace cg = cooperative_groups;
 
 // ----------------------------------------------------------------------------
 // prep: means + window + twiddles
@@ -16,25 +19,42 @@ struct PlanDesc {
     int r[4];
 };
 
+// A clip's mean is summed by a thread-block cluster of `prep_segments(N)` CTAs, one segment of the clip each; the
+// segment totals meet in CTA 0 of the cluster over distributed shared memory and are added in segment order.  The
+// split depends on N alone, so a clip's mean (hence its spectrogram) is bit-identical whatever batch it is part of.
+constexpr int PREP_SEG_POINTS = 32768;
+constexpr int PREP_MAX_SEGMENTS = 8;   // portable cluster size
+__host__ __device__ inline int prep_segments(int N) {
+    const int s = (N + PREP_SEG_POINTS - 1) / PREP_SEG_POINTS;
+    return s < 1 ? 1 : (s > PREP_MAX_SEGMENTS ? PREP_MAX_SEGMENTS : s);
+}
+
+// grid = (B + 1) clusters of prep_segments(N) CTAs: cluster b < B -> mean of clip b; cluster B -> window + twiddles
 __global__ void __launch_bounds__(PREP_THREADS)
 dmel_prep_kernel(const float* __restrict__ x, long long x_stride, int B, int N, float lam_abs, int win_length,
                  int n_fft, int flags, WsView ws, PlanDesc plan) {
     __shared__ double red[32];
+    __shared__ double seg_total;
     const int tid = threadIdx.x;
     const int normalize = flags & DMEL_FLAG_NORMALIZE_WINDOW;
-    if (int(blockIdx.x) < B) {
+    const int nseg = prep_segments(N);
+    const int clip = int(blockIdx.x) / nseg, seg = int(blockIdx.x) - clip * nseg;
+    if (clip < B) {
         if (flags & DMEL_FLAG_KEEP_MEAN) {
-            if (tid == 0) ws.means[blockIdx.x] = 0.f;
+            if (tid == 0 && seg == 0) ws.means[clip] = 0.f;
             return;
         }
         // models.py:38  x[idx] - torch.mean(x[idx])
-        const float* xb = x + (long long)blockIdx.x * x_stride;
+        const int seg_len = (((N + nseg - 1) / nseg) + 3) & ~3;       // multiple of 4: segments keep x's alignment
+        const int lo = min(seg * seg_len, N), hi = min(lo + seg_len, N);
+        const float* xb = x + (long long)clip * x_stride + lo;
+        const int n = hi - lo;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int i0 = 0;
         if ((reinterpret_cast<uintptr_t>(xb) & 15) == 0) {
             // 16-byte loads, 8 independent ones in flight per thread
             const float4* x4 = reinterpret_cast<const float4*>(xb);
-            const int n4 = N >> 2;
+            const int n4 = n >> 2;
             int q = tid;
             for (; q + 7 * PREP_THREADS < n4; q += 8 * PREP_THREADS) {
                 float4 v[8];
@@ -49,14 +69,25 @@ dmel_prep_kernel(const float* __restrict__ x, long long x_stride, int B, int N, 
             }
             i0 = n4 << 2;
         }
-        for (int i = i0 + tid; i < N; i += PREP_THREADS) acc[1] += __ldg(xb + i);
+        for (int i = i0 + tid; i < n; i += PREP_THREADS) acc[1] += __ldg(xb + i);
         double part = 0.0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) part += double(acc[u]);
         double tot = block_sum(part, red);
-        if (tid == 0) ws.means[blockIdx.x] = float(tot / double(N));
+        if (nseg > 1) {
+            cg::cluster_group cluster = cg::this_cluster();
+            if (tid == 0) seg_total = tot;
+            cluster.sync();
+            if (seg == 0 && tid == 0) {
+                tot = 0.0;
+                for (int r = 0; r < nseg; ++r) tot += *cluster.map_shared_rank(&seg_total, r);
+            }
+            cluster.sync();     // a CTA's shared memory must outlive the remote reads of it
+        }
+        if (tid == 0 && seg == 0) ws.means[clip] = float(tot / double(N));
         return;
     }
+    if (seg != 0) return;
     // time_frequency.py:21-30; torch.stft centre-pads the window to n_fft
     const int left = (n_fft - win_length) / 2;
     const float lam = lam_abs + 1e-15f;

@@ -40,6 +40,7 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __res
     const bool row_aligned = g.row_aligned != 0;
     const int tt_shift = ilog2(g.TT);
     const bool do_log = g.log_eps >= 0.f;
+    const bool affine = !SPEC && mel.out_scale != nullptr;
     float inv_lam3 = 0.f, cprime = 0.f, centre = 0.f;
     if (JVP) { inv_lam3 = hdr->inv_lam3; cprime = hdr->cprime; centre = hdr->centre; }
 
@@ -160,29 +161,38 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __res
         __syncthreads();
         // models.py:54 pack into (B,1,M,T), T fastest; optional fused log (models.py:72-73)
         // (with g.time_major the result is (B,1,T,M), M fastest: what MelPANNsNet transposes to, models.py:162)
-        auto emit = [&](int m, int tt, long long off) {
+        // the per-mel output map (dmel.h: out_scale/out_shift) is compiled as a second copy of the loops so the
+        // plain path pays nothing for it
+        auto emit = [&](auto aff, int m, int tt, long long off) {
+            constexpr bool AFF = decltype(aff)::value;
             float val = tile[m * TS + tt];
             if (JVP) {
                 // d log(mel + eps) / d|lambda| = dmel / (mel + eps)
-                const float dv = tile2[m * TS + tt];
-                dy[off] = do_log ? __fdividef(dv, val + g.log_eps) : dv;
+                float dv = tile2[m * TS + tt];
+                if (do_log) dv = __fdividef(dv, val + g.log_eps);
+                dy[off] = AFF ? dv * __ldg(mel.out_scale + m) : dv;
             }
             // lg2.approx * ln2: <= 3 ulp, i.e. ~1e-6 absolute on log-mel values (budget 1e-5 + 1e-4 |y|)
             if (do_log) val = __logf(val + g.log_eps);
+            if (AFF) val = affine_out(mel, m, val);
             y[off] = val;
             ysum += val;
         };
-        if (!g.time_major) {
-            const long long base = (long long)b * g.M * g.T + t0;
-            for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
-                const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
-                if (tt < nfr) emit(m, tt, base + (long long)m * g.T + tt);
+        auto emit_tile = [&](auto aff) {
+            if (!g.time_major) {
+                const long long base = (long long)b * g.M * g.T + t0;
+                for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
+                    const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
+                    if (tt < nfr) emit(aff, m, tt, base + (long long)m * g.T + tt);
+                }
+            } else {
+                const long long base = ((long long)b * g.T + t0) * g.M;
+                for (int tt = tid >> 5; tt < nfr; tt += NT / 32)
+                    for (int m = tid & 31; m < g.M; m += 32) emit(aff, m, tt, base + (long long)tt * g.M + m);
             }
-        } else {
-            const long long base = ((long long)b * g.T + t0) * g.M;
-            for (int tt = tid >> 5; tt < nfr; tt += NT / 32)
-                for (int m = tid & 31; m < g.M; m += 32) emit(m, tt, base + (long long)tt * g.M + m);
-        }
+        };
+        if (affine) emit_tile(BoolTag<true>{});
+        else emit_tile(BoolTag<false>{});
         // the next iteration's staging only writes xs; its __syncthreads orders it after this epilogue
     }
     cp_async_wait_all();
@@ -223,6 +233,7 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
     const bool row_aligned = g.row_aligned != 0;
     const int tt_shift = ilog2(g.TT);
     const bool do_log = g.log_eps >= 0.f;
+    const bool affine = !SPEC && mel.out_scale != nullptr;
 
     stage_table_async<NT>(smem_f + lay.twt, tw_g, 2 * TWN, tid);
     stage_table_async<NT>(win, win_g, L, tid);
@@ -295,17 +306,23 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
             for (int i = gtid; i < g.sub_span; i += GT) priv[i] = 0.f;
         cp_async_wait_all();
         span_centre<NT>(xs_cur, p0, g.span, g.N, mu, tid);
-        if (do_log) {
+        if (do_log || affine) {
             // dL/dmel = G / (mel + eps) = G * exp(-y); each thread touches the words it copied itself
-            if (!g.time_major) {
-                for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
-                    const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
-                    gtc[m * TS + tt] *= __expf(-ytc[m * TS + tt]);
+            auto to_dmel = [&](auto aff) {
+                constexpr bool AFF = decltype(aff)::value;
+                auto one = [&](int m, int tt) {
+                    const int i = m * TS + tt;
+                    gtc[i] *= AFF ? affine_grad_factor(mel, m, do_log ? ytc[i] : 0.f, do_log) : __expf(-ytc[i]);
+                };
+                if (!g.time_major) {
+                    for (int idx = tid; idx < (g.M << tt_shift); idx += NT) one(idx >> tt_shift, idx & (g.TT - 1));
+                } else {
+                    for (int tt = tid >> 5; tt < g.TT; tt += NT / 32)
+                        for (int m = tid & 31; m < g.M; m += 32) one(m, tt);
                 }
-            } else {
-                for (int tt = tid >> 5; tt < g.TT; tt += NT / 32)
-                    for (int m = tid & 31; m < g.M; m += 32) gtc[m * TS + tt] *= __expf(-ytc[m * TS + tt]);
-            }
+            };
+            if (affine) to_dmel(BoolTag<true>{});
+            else to_dmel(BoolTag<false>{});
         }
         __syncthreads();   // also: every warp is done with the previous tile
         if (ahead && tix + int(gridDim.x) < total_tiles) issue_tile(tix + gridDim.x, slot ^ 1);

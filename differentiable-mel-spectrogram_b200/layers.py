@@ -70,6 +70,38 @@ class MelSpectrogramLayer(nn.Module):
         self._mirror = _LambdaMirror()
         # 0-d fp64 device tensor: sum of the last forward's output, produced inside the kernel (train.py:58)
         self.last_energy = None
+        # optional per-mel output map (set_output_affine / fold_batchnorm); plain attributes, not buffers, so the
+        # state_dict stays exactly {'lambd'} (utils.py:269-270)
+        self._out_affine = None
+
+    def set_output_affine(self, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor] = None) -> None:
+        """Fold y <- scale[m]*y + shift[m] (per mel bin, after the optional log) into the kernel epilogue; `None`
+        removes it.  The vectors are constants: no gradient flows to them."""
+        if scale is None:
+            self._out_affine = None
+            return
+        scale = scale.detach().to(torch.float32).reshape(-1).clone()
+        shift = torch.zeros_like(scale) if shift is None else shift.detach().to(torch.float32).reshape(-1).clone()
+        if scale.numel() != self.n_mels or shift.numel() != self.n_mels:
+            raise ValueError(f"output affine needs n_mels={self.n_mels} values per vector")
+        self._out_affine = (scale, shift)
+
+    def fold_batchnorm(self, bn: nn.BatchNorm2d) -> None:
+        """Fold an eval-mode BatchNorm over mel bins — `Cnn6.bn1`, applied to the transposed log-mel first thing in
+        the PANNs head (panns.py:146, 169-172) — into the epilogue: the head then skips its `bn1` (and, with
+        `time_major=True`, its transposes).  Uses the running statistics as they are now; call again after loading
+        new weights.  Training-mode BatchNorm (batch statistics) cannot be folded."""
+        if bn.num_features != self.n_mels:
+            raise ValueError(f"BatchNorm has {bn.num_features} features, the layer has n_mels={self.n_mels}")
+        if bn.running_mean is None or bn.running_var is None:
+            raise ValueError("BatchNorm without running statistics cannot be folded")
+        with torch.no_grad():
+            inv = torch.rsqrt(bn.running_var.to(torch.float32) + bn.eps)
+            scale = inv * bn.weight.to(torch.float32) if bn.weight is not None else inv
+            shift = -bn.running_mean.to(torch.float32) * scale
+            if bn.bias is not None:
+                shift = shift + bn.bias.to(torch.float32)
+        self.set_output_affine(scale, shift)
 
     def forward(self, x):
         dev = _resolve_device(self.device, self.lambd)
@@ -88,8 +120,14 @@ class MelSpectrogramLayer(nn.Module):
                                    normalize_window=self.normalize_window, n_mels=self.n_mels,
                                    sample_rate=self.sample_rate, f_min=self.f_min, f_max=self.f_max,
                                    log_eps=self.log_eps, lambd_value=self._mirror.get(self.lambd), return_energy=True,
-                                   time_major=self.time_major)
+                                   time_major=self.time_major, out_affine=self._affine_on(dev))
         return y
+
+    def _affine_on(self, dev: torch.device):
+        aff = self._out_affine
+        if aff is not None and aff[0].device != dev:
+            aff = self._out_affine = (aff[0].to(dev), aff[1].to(dev))
+        return aff
 
     def invalidate_lambda_cache(self) -> None:
         """Force the next forward to re-read `lambd` from the device.  Only needed after writes that bypass

@@ -135,6 +135,32 @@ class DeviceBank:
     def ref(self):
         return ctypes.byref(self.struct)
 
+    def with_affine(self, scale: torch.Tensor, shift: torch.Tensor) -> "AffineBank":
+        return AffineBank(self, scale, shift)
+
+
+class AffineBank:
+    """A DeviceBank plus a per-mel output map y <- scale[m]*y + shift[m] (dmel.h: out_scale / out_shift): the
+    eval-mode BatchNorm2d over mel bins that panns.py:169-172 applies first.  Holds the two device vectors alive."""
+
+    def __init__(self, bank: DeviceBank, scale: torch.Tensor, shift: torch.Tensor):
+        m = bank.packed.n_mels
+        vec = []
+        for name, v in (("scale", scale), ("shift", shift)):
+            v = v.detach().to(device=bank.device, dtype=torch.float32).reshape(-1).contiguous()
+            if v.numel() != m:
+                raise ValueError(f"out_affine {name} must hold n_mels={m} values, got {v.numel()}")
+            vec.append(v)
+        self.bank, self.packed, self.device = bank, bank.packed, bank.device
+        self.scale, self.shift = vec
+        s = MelBankStruct()
+        ctypes.memmove(ctypes.byref(s), ctypes.byref(bank.struct), ctypes.sizeof(MelBankStruct))
+        s.out_scale, s.out_shift = self.scale.data_ptr(), self.shift.data_ptr()
+        self.struct = s
+
+    def ref(self):
+        return ctypes.byref(self.struct)
+
 
 _cache: Dict[tuple, DeviceBank] = {}
 _cache_lock = threading.Lock()

@@ -202,7 +202,8 @@ class DmelFunction(torch.autograd.Function):
 def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bool,
          normalize_window: bool = False, n_mels: int = 0, sample_rate: int = 0, f_min: float = 0.0,
          f_max: Optional[float] = None, log_eps: Optional[float] = None, remove_mean: bool = True,
-         lambd_value: Optional[float] = None, return_energy: bool = False, time_major: bool = False):
+         lambd_value: Optional[float] = None, return_energy: bool = False, time_major: bool = False,
+         out_affine: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
     """Functional form of both layers.
 
     x: (B, N) CUDA tensor (fp32; fp64/fp16 inputs are cast to fp32 — the reference's fp64
@@ -214,6 +215,9 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
     the result is `(y, energy)`, energy a 0-d fp64 device tensor = y.sum() computed inside the forward kernel
     (what train.py:58 copies the whole spectrogram batch to the host for).  `time_major=True` returns
     (B, 1, N//hop + 1, rows) instead — the layout MelPANNsNet transposes to before Cnn6 (models.py:162).
+    `out_affine=(scale, shift)` (two vectors of n_mels values, mel mode only) folds y <- scale[m]*y + shift[m] into the
+    kernel epilogue, after the log: the eval-mode BatchNorm2d over mel bins that Cnn6 applies first (panns.py:169-172).
+    The pair is a constant of the call (no gradient flows to it); gradients to x and lambd pass through it.
     """
     if x.dim() != 2:
         raise ValueError(f"expected x of shape (batch, n_points), got {tuple(x.shape)}")
@@ -255,11 +259,26 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
             _plan_cache.clear()
         _plan_cache[key] = plan
     geo, bank, eps, flags = plan
+    if out_affine is not None:
+        if bank is None:
+            raise ValueError("out_affine needs n_mels > 0 (it is a per-mel map)")
+        # the struct only holds the two pointers: reuse it while the same vectors come back (the layers keep theirs)
+        direct = all(v.dtype == torch.float32 and v.device == x.device and v.is_contiguous() for v in out_affine)
+        akey = (id(bank), out_affine[0].data_ptr(), out_affine[1].data_ptr())
+        abank = _affine_cache.get(akey) if direct else None
+        if abank is None:
+            abank = bank.with_affine(*out_affine)     # converts / copies whatever is not fp32 on x's device
+            if direct:
+                if len(_affine_cache) > 16:
+                    _affine_cache.clear()
+                _affine_cache[akey] = abank
+        bank = abank
     y, energy = DmelFunction.apply(x, lambd, geo, bank, eps, flags, lam_value)
     return (y, energy) if return_energy else y
 
 
 _plan_cache: dict = {}
+_affine_cache: dict = {}
 
 
 def query_launch(batch: int, n_points: int, n_fft: int, hop: int, rows: int, bank_nnz: int = 0,

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DMEL_ABI_VERSION 1
+#define DMEL_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DMEL_API __attribute__((visibility("default")))
@@ -62,7 +62,15 @@ typedef enum dmel_status {
  *       cnt = bin_off[k+1]-bin_off[k], weights bin_w[bin_off[k] + i]
  * All six arrays are device pointers, each 16-byte aligned and readable up to the next
  * multiple of 4 elements (they are staged into shared memory with 16-byte async copies);
- * the struct itself lives on the host.                                              */
+ * the struct itself lives on the host.
+ *
+ * out_scale / out_shift (both NULL, or both device arrays of n_mels floats) fold a per-mel
+ * affine map into the epilogue:  y[b,0,m,t] <- out_scale[m] * y[b,0,m,t] + out_shift[m],
+ * applied after the optional log.  This is the eval-mode BatchNorm2d over mel bins that the
+ * PANNs head applies first (panns.py:169-172): scale = gamma/sqrt(var+eps), shift = beta -
+ * mean*scale.  The backward takes grad_y with respect to the mapped output and, when the log
+ * is fused, recovers log-mel as (y - shift)/scale (a mel whose scale is 0 gets no gradient).
+ * The map is a constant of the call: no gradient is produced for it.                  */
 typedef struct dmel_melbank {
     int32_t n_freqs;          /* F = n_fft/2 + 1                                        */
     int32_t n_mels;           /* M                                                      */
@@ -74,6 +82,8 @@ typedef struct dmel_melbank {
     const int32_t* bin_m0;    /* [F]                                                    */
     const int32_t* bin_off;   /* [F+1]                                                  */
     const float* bin_w;       /* [bin_off[F]]                                           */
+    const float* out_scale;   /* [M] or NULL                                            */
+    const float* out_shift;   /* [M] or NULL                                            */
 } dmel_melbank;
 
 DMEL_API int dmel_abi_version(void);

@@ -394,3 +394,70 @@ def test_time_frequency_function_mirror(cuda_device):
                                            return_window=True)
     check_y(got.cpu().numpy(), want.numpy(), True)
     np.testing.assert_allclose(w.cpu().numpy(), orc.gaussian_window(torch.tensor(23.0), 256, False).numpy(), rtol=1e-6)
+
+
+def _random_eval_bn(M, seed):
+    g = torch.Generator().manual_seed(seed)
+    bn = torch.nn.BatchNorm2d(M).eval()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(M, generator=g) * 1.5 + 0.25)
+        bn.weight[::7] *= -1.0                                  # negative gains are legal
+        bn.bias.copy_(torch.randn(M, generator=g))
+        bn.running_mean.copy_(torch.randn(M, generator=g) * 3.0 - 2.0)
+        bn.running_var.copy_(torch.rand(M, generator=g) * 4.0 + 0.5)
+    return bn
+
+
+@pytest.mark.parametrize("B,N,sr,hop,M,lam,optimized,use_log,tm", [
+    (8, 8000, 8000, 80, 64, 46.667, True, True, False),         # tiled FFT path, n_fft 512
+    (8, 8000, 8000, 80, 64, 46.667, True, True, True),          #   ... emitting (B,1,T,M) as Cnn6 takes it
+    (8, 8000, 8000, 80, 64, 46.667, True, False, False),        #   ... linear mel power
+    (3, 22050, 44100, 441, 128, 257.25, True, True, True),      # esc50 clip shape (short), n_fft 2048
+    (2, 32000, 16000, 160, 128, 16000 * 0.300 / 6, True, True, False),   # big-FFT path, n_fft 8192
+    (4, 100, 8000, 10, 16, 5.0, False, True, False),            # direct-DFT path, n_fft 200
+])
+def test_folded_eval_batchnorm_matches_batchnorm_after_the_layer(cuda_device, B, N, sr, hop, M, lam, optimized, use_log, tm):
+    """Cnn6 starts with BatchNorm2d over mel bins on the transposed log-mel (panns.py:169-172).  In
+    eval mode that is a per-mel affine map; folded into the epilogue it must equal the real BatchNorm2d applied to
+    the oracle's output, with the same gradients to x and lambd."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(B, N, generator=g)
+    bn = _random_eval_bn(M, 7)
+    kw_o = dict(hop=hop, optimized=optimized, norm=False, n_mels=M, sample_rate=sr)
+    with torch.no_grad():
+        y0 = orc.port_forward_batched(x, torch.tensor(lam), **kw_o)             # (B,1,M,T) linear mel power
+        if use_log:
+            y0 = torch.log(y0 + EPS)
+        want_y = bn(y0.transpose(1, 2)).transpose(1, 2)                         # channels = mel bins
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    G = torch.randn(want_y.shape, generator=g)
+    # BatchNorm in eval mode is affine per mel: the gradient reaching the layer is G * scale[m]
+    _, dx0, dlam0 = orc.port_forward_backward(x, lam, G * scale.view(1, 1, M, 1), use_log=use_log, batched=True, **kw_o)
+
+    layer = dm.MelSpectrogramLayer(torch.tensor(lam), n_mels=M, n_points=N, sample_rate=sr, hop_length=hop, device="cuda:0",
+                                   optimized=optimized, log_eps=EPS if use_log else None, time_major=tm).to(dev)
+    layer.fold_batchnorm(bn)
+    assert list(layer.state_dict()) == ["lambd"]
+    Gd = (G.transpose(2, 3) if tm else G).contiguous().to(dev)
+    for need_dx in (True, False):                     # recomputing backward, then the forward-mode (JVP) path
+        layer.lambd.grad = None
+        xin = x.to(dev).requires_grad_(need_dx)
+        y = layer(xin)
+        (y * Gd).sum().backward()
+        got = y.detach().transpose(2, 3) if tm else y.detach()
+        span = float(want_y.abs().max())
+        np.testing.assert_allclose(got.cpu().numpy(), want_y.numpy(), rtol=Y_RTOL,
+                                   atol=Y_ATOL * (max(1.0, span) if use_log else span))
+        assert abs(float(layer.last_energy) - float(y.double().sum())) <= 1e-6 * float(y.double().abs().sum())
+        dlam = float(layer.lambd.grad)
+        assert abs(dlam - dlam0) <= G_RTOL * abs(dlam0), (dlam, dlam0)
+        if need_dx:
+            assert rel_err(xin.grad.cpu().numpy(), dx0) < G_RTOL
+    # removing the map restores the plain output
+    layer.set_output_affine(None)
+    with torch.no_grad():
+        y_plain = layer(x.to(dev))
+    y_plain = y_plain.transpose(2, 3) if tm else y_plain
+    np.testing.assert_allclose(y_plain.cpu().numpy(), y0.numpy(), rtol=Y_RTOL,
+                               atol=Y_ATOL * (1.0 if use_log else float(y0.abs().max())))

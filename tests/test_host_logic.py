@@ -20,7 +20,7 @@ def test_library_loads_and_exports_header_symbols():
     assert declared == set(dm._lib.EXPORTED_SYMBOLS), declared ^ set(dm._lib.EXPORTED_SYMBOLS)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.dmel_abi_version() == 1
+    assert lib.dmel_abi_version() == 2
     assert lib.dmel_status_string(0) == b"ok"
     assert b"n_fft" in lib.dmel_status_string(-3)
 
@@ -90,6 +90,41 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_device():
     # odd n_fft has no kernel
     assert lib.dmel_nfft_supported(255) == 0 and lib.dmel_nfft_supported(512) == 1 and lib.dmel_nfft_supported(200) == 1
     assert lib.dmel_workspace_bytes(256, 512) >= 64 + 512 * 12 + 256 * 12
+
+
+def test_output_affine_struct_fields_and_batchnorm_folding():
+    # struct dmel_melbank: 4 int32 + 8 pointers (include/dmel.h)
+    assert ctypes.sizeof(dm._lib.MelBankStruct) == 4 * 4 + 8 * 8
+    assert [f[0] for f in dm._lib.MelBankStruct._fields_][-2:] == ["out_scale", "out_shift"]
+    # a bank with only one of the two vectors is rejected before anything touches the device
+    lib = dm.load()
+    s = dm._lib.MelBankStruct()
+    s.n_freqs, s.n_mels, s.mel_nnz, s.bin_nnz = 33, 4, 16, 40
+    s.mel_k0 = s.mel_off = s.mel_w = s.bin_m0 = s.bin_off = s.bin_w = 16
+    s.out_scale, s.out_shift = 16, None
+    f = lib.dmel_forward_f32
+    assert f(8, 1, 100, 100, 10.0, 64, 64, 10, 4, ctypes.byref(s), -1.0, 0, 8, 8, 1 << 20, None) == -7
+    # eval-mode BatchNorm2d over mel bins == per-mel affine map (panns.py:146, 169-172)
+    M = 8
+    bn = torch.nn.BatchNorm2d(M).eval()
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(M, generator=g)); bn.bias.copy_(torch.randn(M, generator=g))
+        bn.running_mean.copy_(torch.randn(M, generator=g)); bn.running_var.copy_(torch.rand(M, generator=g) + 0.1)
+    layer = dm.MelSpectrogramLayer(torch.tensor(20.0), n_mels=M, n_points=800, sample_rate=8000, hop_length=80, optimized=True)
+    layer.fold_batchnorm(bn)
+    scale, shift = layer._out_affine
+    y = torch.randn(3, 1, M, 11, generator=g)
+    with torch.no_grad():
+        want = bn(y.transpose(1, 2)).transpose(1, 2)
+    assert torch.allclose(y * scale.view(1, 1, M, 1) + shift.view(1, 1, M, 1), want, rtol=1e-6, atol=1e-6)
+    assert list(layer.state_dict()) == ["lambd"]
+    with pytest.raises(ValueError):
+        layer.fold_batchnorm(torch.nn.BatchNorm2d(M + 1))
+    with pytest.raises(ValueError):
+        layer.set_output_affine(torch.ones(M), torch.zeros(M - 1))
+    layer.set_output_affine(None)
+    assert layer._out_affine is None
 
 
 def test_fft_plan_swizzle_is_xor_separable():
