@@ -82,6 +82,17 @@ struct MelDev {
     const float* out_shift;
 };
 
+// Frames handled by each of the NG groups of a tile holding nfr (<= TT = NG*SF) frames.  Full tiles: SF.  The
+// short last tile of a clip is split evenly instead (a multiple of 2 when frames travel as packed pairs), so its
+// transforms run side by side on all groups rather than one after the other on the first ones.
+template <int NG, bool PAIRS>
+__device__ __forceinline__ int tile_frames_per_group(int nfr, int TT, int SF) {
+    if (NG == 1 || nfr >= TT) return SF;
+    int s = (nfr + NG - 1) / NG;
+    if (PAIRS) s = (s + 1) & ~1;
+    return s;
+}
+
 template <bool V> struct BoolTag { static constexpr bool value = V; };
 
 // forward epilogue: y <- scale[m]*y + shift[m]

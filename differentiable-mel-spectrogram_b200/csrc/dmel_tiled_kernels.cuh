@@ -92,8 +92,10 @@ dmel_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __res
             }
         }
 
-        const int f_hi = min(grp * g.SF + g.SF, nfr);
-        for (int f = grp * g.SF; f < f_hi; f += (JVP ? 1 : 2)) {
+        // frames per group: a short last tile of a clip is re-split evenly over the groups (whole pairs)
+        const int sfe = tile_frames_per_group<NG, !JVP>(nfr, g.TT, g.SF);
+        const int f_hi = min(grp * sfe + sfe, nfr);
+        for (int f = grp * sfe; f < f_hi; f += (JVP ? 1 : 2)) {
             const float* xa = xs + f * g.hop;
             const float* xb2 = xa + g.hop;
             float2 v[E];
@@ -327,8 +329,9 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
         __syncthreads();   // also: every warp is done with the previous tile
         if (ahead && tix + int(gridDim.x) < total_tiles) issue_tile(tix + gridDim.x, slot ^ 1);
 
-        const int f_lo = grp * g.SF;
-        const int f_hi = min(f_lo + g.SF, nfr);
+        const int sfe = tile_frames_per_group<NG, true>(nfr, g.TT, g.SF);   // short last tile: even re-split
+        const int f_lo = grp * sfe;
+        const int f_hi = min(f_lo + sfe, nfr);
         for (int f = f_lo; f < f_hi; f += 2) {
             const float* xa = xs + f * g.hop;
             const float* xb2 = xa + g.hop;
@@ -429,7 +432,7 @@ dmel_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
             const int excl_hi = (tile_i == g.tiles_per_clip - 1) ? g.N : (t0 + nfr) * g.hop - L / 2;
             float* dxb = dx + (long long)b * g.N;
             const float* priv0 = smem_f + lay.grp + 2 * L;
-            const int gstep = g.SF * g.hop;
+            const int gstep = sfe * g.hop;
             float part = 0.f;
             for (int i = tid; i < span_used; i += NT) {
                 const int p = p0 + i;

@@ -461,3 +461,42 @@ def test_folded_eval_batchnorm_matches_batchnorm_after_the_layer(cuda_device, B,
     y_plain = y_plain.transpose(2, 3) if tm else y_plain
     np.testing.assert_allclose(y_plain.cpu().numpy(), y0.numpy(), rtol=Y_RTOL,
                                atol=Y_ATOL * (1.0 if use_log else float(y0.abs().max())))
+
+
+def test_layer_forward_backward_can_be_captured_in_a_cuda_graph(cuda_device):
+    """The op allocates through torch's allocator, never synchronises and reads lambd from the host mirror while the
+    parameter is unchanged, so a whole training-style step of the layer can live in a CUDA graph."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    layer = dm.MelSpectrogramLayer(torch.tensor(46.667), n_mels=64, n_points=8000, sample_rate=8000, hop_length=80,
+                                   device="cuda:0", optimized=True, log_eps=EPS).to(dev)
+    x_static = torch.randn(16, 8000, generator=g).to(dev)
+    G = torch.randn(16, 1, 64, 101, generator=g).to(dev)
+
+    def step():
+        layer.lambd.grad = None
+        y = layer(x_static)
+        (y * G).sum().backward()
+        return y
+
+    s = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(s):
+        for _ in range(3):                        # warm-up on a side stream, as torch.cuda.graph wants
+            step()
+    torch.cuda.current_stream(dev).wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    layer.lambd.grad = None
+    with torch.cuda.graph(graph):
+        y_static = layer(x_static)
+        (y_static * G).sum().backward()
+    grad_static = layer.lambd.grad
+    for seed in (11, 12):
+        x_new = torch.randn(16, 8000, generator=torch.Generator().manual_seed(seed)).to(dev)
+        x_static.copy_(x_new)
+        graph.replay()
+        torch.cuda.synchronize()
+        got_y, got_g = y_static.clone(), float(grad_static)
+        want_y = step()
+        assert torch.equal(got_y, want_y.detach())
+        assert abs(got_g - float(layer.lambd.grad)) <= 1e-6 * abs(got_g)
