@@ -189,7 +189,8 @@ def load() -> ctypes.CDLL:
                 f"{LIB_PATH} not found — run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(or `make -C differentiable-mel-spectrogram_b200/csrc`). There is no CPU fallback."
             )
-        lib = ctypes.CDLL(LIB_PATH)
+        # DMEL_LIB_PATH: load another build of the same ABI (kernel experiments)
+        lib = ctypes.CDLL(os.environ.get("DMEL_LIB_PATH") or LIB_PATH)
         missing = [s for s in EXPORTED_SYMBOLS if not hasattr(lib, s)]
         if missing:
             raise DmelError(f"{LIB_PATH} does not export {missing}")
