@@ -245,7 +245,8 @@ def test_strided_rows_fp16_input_and_negative_lambda(cuda_device):
     check_y(yh.detach().cpu().numpy(), w.numpy(), True)
 
 
-@pytest.mark.parametrize("offset,N", [(1, 1600), (2, 1603), (3, 4001), (101, 1599)])
+@pytest.mark.parametrize("offset,N", [(1, 1600), (2, 1603), (3, 4001), (101, 1599),
+                                      (1, 70001), (0, 98306)])   # > 32768 points: the mean is summed by a CTA cluster
 def test_unaligned_input_rows_take_the_scalar_copy_path(cuda_device, offset, N):
     """x rows that are only 4-byte aligned (a column slice of a bigger buffer): the 16-byte async copies must not be used."""
     dev = cuda_device
@@ -500,3 +501,26 @@ def test_layer_forward_backward_can_be_captured_in_a_cuda_graph(cuda_device):
         want_y = step()
         assert torch.equal(got_y, want_y.detach())
         assert abs(got_g - float(layer.lambd.grad)) <= 1e-6 * abs(got_g)
+
+
+def test_per_clip_mean_is_batch_invariant_and_exact_for_long_clips(cuda_device):
+    """models.py:38 removes each clip's mean.  Clips longer than 32768 points are summed by a cluster of CTAs whose
+    split depends on N only: the same clip gives bit-identical output alone or inside a batch, and a large DC offset
+    (1e3 x the signal) is removed to fp32 accuracy (the sum is carried in fp64)."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(17)
+    N = 220500
+    x = torch.randn(5, N, generator=g) + torch.tensor([0.0, 1000.0, -1000.0, 3.0, 0.5]).view(5, 1)
+    kw = dict(hop_length=441, optimized=True, n_mels=128, sample_rate=44100, log_eps=EPS)
+    ll = torch.tensor(257.25, device=dev)
+    xd = x.to(dev)
+    with torch.no_grad():
+        y_all = dm.dmel(xd, ll, **kw)
+        for i in range(5):
+            assert torch.equal(dm.dmel(xd[i:i + 1], ll, **kw), y_all[i:i + 1])
+        # same clips with the offset removed in fp64 on the host
+        x0 = (x.double() - x.double().mean(dim=1, keepdim=True)).float().to(dev)
+        y_ref = dm.dmel(x0, ll, **kw)
+    # the offset clips lost ~10 bits of signal mantissa to the DC before reaching the kernel; compare the rest
+    np.testing.assert_allclose(y_all[[0, 3, 4]].cpu().numpy(), y_ref[[0, 3, 4]].cpu().numpy(), rtol=Y_RTOL, atol=2e-4)
+    np.testing.assert_allclose(y_all[[1, 2]].cpu().numpy(), y_ref[[1, 2]].cpu().numpy(), rtol=0, atol=0.05)
