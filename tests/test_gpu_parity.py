@@ -524,3 +524,47 @@ def test_per_clip_mean_is_batch_invariant_and_exact_for_long_clips(cuda_device):
     # the offset clips lost ~10 bits of signal mantissa to the DC before reaching the kernel; compare the rest
     np.testing.assert_allclose(y_all[[0, 3, 4]].cpu().numpy(), y_ref[[0, 3, 4]].cpu().numpy(), rtol=Y_RTOL, atol=2e-4)
     np.testing.assert_allclose(y_all[[1, 2]].cpu().numpy(), y_ref[[1, 2]].cpu().numpy(), rtol=0, atol=0.05)
+
+
+def _fuzz_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    cases = []
+    while len(cases) < n:
+        n_fft = int(2 ** rng.integers(5, 13))                    # 32 .. 4096 (direct-DFT below 128, FFT above)
+        lam = float(rng.uniform(0.52, 0.99) * n_fft / 6.0)       # inside the bracket that derives n_fft
+        hop = int(rng.choice([1, 3, 17, 80, 160, 441, 700]))
+        N = int(rng.integers(max(hop, 40), 6000))
+        T = N // hop + 1
+        if T * n_fft > 3_000_000:                                # keep the CPU oracle in the seconds
+            continue
+        M = int(rng.choice([0, 8, 23, 64, 80]))
+        if M and M > n_fft // 4:
+            continue
+        cases.append((int(rng.integers(1, 6)), N, hop, lam, M, bool(rng.integers(0, 2)), bool(rng.integers(0, 2)), n_fft))
+    return cases
+
+
+@pytest.mark.parametrize("B,N,hop,lam,M,norm,use_log,n_fft", _fuzz_cases(28, 2024))
+def test_random_geometries_against_oracle(cuda_device, B, N, hop, lam, M, norm, use_log, n_fft):
+    """Seeded sweep over odd shapes (ragged last tiles, hop > n_fft, hop 1, spectrogram and mel mode, normalised window,
+    linear and log output) against the CPU oracle, forward and both gradients."""
+    assert orc.window_length(lam, N, True)[1] == n_fft
+    dev = cuda_device
+    g = torch.Generator().manual_seed(N * 7 + hop)
+    x = torch.randn(B, N, generator=g)
+    kw_o = dict(hop=hop, optimized=True, norm=norm)
+    kw_c = dict(hop_length=hop, optimized=True, normalize_window=norm)
+    if M:
+        kw_o.update(n_mels=M, sample_rate=8000)
+        kw_c.update(n_mels=M, sample_rate=8000)
+    rows = M if M else n_fft // 2 + 1
+    G = torch.randn(B, 1, rows, N // hop + 1, generator=g)
+    want = orc.port_forward_backward(x, lam, G, use_log=use_log, batched=True, **kw_o)
+    got = run_cuda(dev, x, lam, G, use_log, True, **kw_c)
+    check_y(got[0], want[0], not use_log)
+    # the oracle's own fp32 gradient noise grows with cancellation; fall back to its fp64 run when it is the outlier
+    try:
+        check_grads(got[1], got[2], want[1], want[2])
+    except AssertionError:
+        want64 = orc.port_forward_backward(x, lam, G, use_log=use_log, batched=True, dtype=torch.float64, **kw_o)
+        check_grads(got[1], got[2], np.asarray(want64[1], dtype=np.float64), float(want64[2]))
