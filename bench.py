@@ -420,33 +420,45 @@ def main():
         Rh = min(R, 4)
         hgen = torch.Generator().manual_seed(1234 + rank)
         host_x = [torch.randn(B, N, generator=hgen).pin_memory() for _ in range(Rh)]
-        host_out = torch.zeros(2, 2).pin_memory()
-        xdev = [torch.empty(B, N, device=dev) for _ in range(2)]
-        copy_stream = torch.cuda.Stream(dev)
-        ready = [torch.cuda.Event() for _ in range(2)]
-        free = [torch.cuda.Event() for _ in range(2)]
+        host_out = torch.zeros(2).pin_memory()
+        host_slot = [host_out[k] for k in range(2)]
+        # three device buffers and two copy streams: uploads i and i+1 overlap each other (one 8 MB copy alone reaches
+        # ~41 GB/s on this box, two in flight ~54 GB/s) and the compute of batch i-1
+        NB_E2E = 3
+        xdev = [torch.empty(B, N, device=dev) for _ in range(NB_E2E)]
+        copy_streams = [torch.cuda.Stream(dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(NB_E2E)]
+        free = [torch.cuda.Event() for _ in range(NB_E2E)]
         main_stream = torch.cuda.current_stream(dev)
 
-        def e2e_loop(k):
-            for i in range(k + 1):
-                if i < k:                      # upload clip batch i while batch i-1 computes
-                    with torch.cuda.stream(copy_stream):
-                        copy_stream.wait_event(free[i % 2])
-                        xdev[i % 2].copy_(host_x[i % Rh], non_blocking=True)
-                        ready[i % 2].record(copy_stream)
-                if i > 0:
-                    j = i - 1
-                    main_stream.wait_event(ready[j % 2])
-                    xin = xdev[j % 2].detach().requires_grad_(True)
+        def pipelined(k, upload, compute):
+            for i in range(k + 2):
+                if i < k:                      # upload clip batch i while batches i-1 / i-2 upload / compute
+                    cs = copy_streams[i % 2]
+                    with torch.cuda.stream(cs):
+                        cs.wait_event(free[i % NB_E2E])
+                        upload(i)
+                        ready[i % NB_E2E].record(cs)
+                j = i - 2
+                if j >= 0:
+                    main_stream.wait_event(ready[j % NB_E2E])
                     layer.lambd.grad = None
-                    y = layer(xin)
-                    y.backward(Gs[j % R])
+                    compute(j)
                     if world > 1:
                         dm.allreduce_lambda_grad([layer.lambd], ring=ring)
-                    free[j % 2].record(main_stream)
-                    # the step's scalar results go back to the host: dL/dlambda and one checksum element of dL/dx
-                    host_out[j % 2, 0].copy_(layer.lambd.grad, non_blocking=True)
-                    host_out[j % 2, 1].copy_(xin.grad[0, 0], non_blocking=True)
+                    free[j % NB_E2E].record(main_stream)
+                    # the step's result goes back to the host: dL/dlambda
+                    host_slot[j % 2].copy_(layer.lambd.grad, non_blocking=True)
+
+        def up_f32(i):
+            xdev[i % NB_E2E].copy_(host_x[i % Rh], non_blocking=True)
+
+        def step_f32(j):
+            xin = xdev[j % NB_E2E].detach().requires_grad_(True)
+            layer(xin).backward(Gs[j % R])
+
+        def e2e_loop(k):
+            pipelined(k, up_f32, step_f32)
 
         for e in free:
             e.record(main_stream)
@@ -463,27 +475,17 @@ def main():
         # the datasets are 16-bit PCM; shipping int16 halves the H2D bytes.  Same loop, host clips
         # as pinned int16, widened to fp32 on the device (one cast) before the layer.  Extra, not the headline.
         host_pcm = [(h * 8192.0).clamp_(-32768, 32767).to(torch.int16).pin_memory() for h in host_x]
-        pdev = [torch.empty(B, N, device=dev, dtype=torch.int16) for _ in range(2)]
+        pdev = [torch.empty(B, N, device=dev, dtype=torch.int16) for _ in range(NB_E2E)]
+
+        def up_pcm(i):
+            pdev[i % NB_E2E].copy_(host_pcm[i % Rh], non_blocking=True)
+
+        def step_pcm(j):
+            xin = pdev[j % NB_E2E].to(torch.float32).requires_grad_(True)
+            layer(xin).backward(Gs[j % R])
 
         def pcm_loop(k):
-            for i in range(k + 1):
-                if i < k:
-                    with torch.cuda.stream(copy_stream):
-                        copy_stream.wait_event(free[i % 2])
-                        pdev[i % 2].copy_(host_pcm[i % Rh], non_blocking=True)
-                        ready[i % 2].record(copy_stream)
-                if i > 0:
-                    j = i - 1
-                    main_stream.wait_event(ready[j % 2])
-                    xin = pdev[j % 2].to(torch.float32).requires_grad_(True)
-                    layer.lambd.grad = None
-                    y = layer(xin)
-                    y.backward(Gs[j % R])
-                    if world > 1:
-                        dm.allreduce_lambda_grad([layer.lambd])
-                    free[j % 2].record(main_stream)
-                    host_out[j % 2, 0].copy_(layer.lambd.grad, non_blocking=True)
-                    host_out[j % 2, 1].copy_(xin.grad[0, 0], non_blocking=True)
+            pipelined(k, up_pcm, step_pcm)
 
         pcm_loop(5)
         barrier()
@@ -545,10 +547,10 @@ def main():
             line["collective_timed_out"] = ring.timed_out()
         if e2e:
             line["e2e"] = {"value": world * audio_s * e2e[1] / (e2e[0] * 1e-3), "unit": UNIT,
-                           "h2d_bytes_per_step": 4 * B * N, "d2h_bytes_per_step": 8, "steps": e2e[1],
-                           "api": "MelSpectrogramLayer.forward + Tensor.backward, pinned host x, double-buffered H2D"}
+                           "h2d_bytes_per_step": 4 * B * N, "d2h_bytes_per_step": 4, "steps": e2e[1],
+                           "api": "MelSpectrogramLayer.forward + Tensor.backward (eager), pinned host x, uploads pipelined over two copy streams"}
             line["e2e_pcm16"] = {"value": world * audio_s * e2e[1] / (ms_pcm * 1e-3), "unit": UNIT,
-                                 "h2d_bytes_per_step": 2 * B * N, "d2h_bytes_per_step": 8,
+                                 "h2d_bytes_per_step": 2 * B * N, "d2h_bytes_per_step": 4,
                                  "note": "same loop with int16 PCM host clips (the datasets' native format), widened to fp32 on "
                                          "the device by one torch cast before the layer; extra, not the headline e2e"}
         if not args.no_cpu_baseline:

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .op import dmel
+from .op import dmel, workspace_energy
 
 
 class _LambdaMirror:
@@ -68,8 +68,7 @@ class MelSpectrogramLayer(nn.Module):
         self.log_eps = log_eps
         self.time_major = time_major      # True: (B, 1, n_time, n_mels), what MelPANNsNet feeds Cnn6 (models.py:162)
         self._mirror = _LambdaMirror()
-        # 0-d fp64 device tensor: sum of the last forward's output, produced inside the kernel (train.py:58)
-        self.last_energy = None
+        self._last_ws = None              # workspace of the last forward: holds the fused energy sum
         # optional per-mel output map (set_output_affine / fold_batchnorm); plain attributes, not buffers, so the
         # state_dict stays exactly {'lambd'} (utils.py:269-270)
         self._out_affine = None
@@ -116,12 +115,18 @@ class MelSpectrogramLayer(nn.Module):
             # the reference fails on the slice assignment models.py:54
             raise RuntimeError(f"input has {n_points} points -> {n_points // self.hop_length + 1} frames, "
                                f"layer was built for n_time={self.n_time}")
-        y, self.last_energy = dmel(x, self.lambd, hop_length=self.hop_length, optimized=self.optimized,
-                                   normalize_window=self.normalize_window, n_mels=self.n_mels,
-                                   sample_rate=self.sample_rate, f_min=self.f_min, f_max=self.f_max,
-                                   log_eps=self.log_eps, lambd_value=self._mirror.get(self.lambd), return_energy=True,
-                                   time_major=self.time_major, out_affine=self._affine_on(dev))
+        y, self._last_ws = dmel(x, self.lambd, hop_length=self.hop_length, optimized=self.optimized,
+                                normalize_window=self.normalize_window, n_mels=self.n_mels,
+                                sample_rate=self.sample_rate, f_min=self.f_min, f_max=self.f_max,
+                                log_eps=self.log_eps, lambd_value=self._mirror.get(self.lambd), return_workspace=True,
+                                time_major=self.time_major, out_affine=self._affine_on(dev))
         return y
+
+    @property
+    def last_energy(self):
+        """0-d fp64 device tensor: sum of the last forward's output, produced inside the kernel — what train.py:58
+        copies the whole spectrogram batch to the host for.  `None` before the first forward."""
+        return None if self._last_ws is None else workspace_energy(self._last_ws)
 
     def _affine_on(self, dev: torch.device):
         aff = self._out_affine
@@ -152,7 +157,12 @@ class SpectrogramLayer(nn.Module):
         self.normalize_window = normalize_window
         self.log_eps = log_eps
         self._mirror = _LambdaMirror()
-        self.last_energy = None
+        self._last_ws = None
+
+    @property
+    def last_energy(self):
+        """See MelSpectrogramLayer.last_energy."""
+        return None if self._last_ws is None else workspace_energy(self._last_ws)
 
     def forward(self, x):
         dev = _resolve_device(self.device, self.lambd)
@@ -162,9 +172,9 @@ class SpectrogramLayer(nn.Module):
                 "fallback; move the module with .to('cuda')")
         if x.device != dev:
             x = x.to(dev, non_blocking=True)
-        s, self.last_energy = dmel(x, self.lambd, hop_length=self.hop_length, optimized=self.optimized,
-                                   normalize_window=self.normalize_window, n_mels=0, log_eps=self.log_eps,
-                                   lambd_value=self._mirror.get(self.lambd), return_energy=True)
+        s, self._last_ws = dmel(x, self.lambd, hop_length=self.hop_length, optimized=self.optimized,
+                                normalize_window=self.normalize_window, n_mels=0, log_eps=self.log_eps,
+                                lambd_value=self._mirror.get(self.lambd), return_workspace=True)
         if self.optimized and tuple(s.shape[2:]) != tuple(self.size):
             # models.py:186,198: the reference allocates `size` and assigns the (F, T) spectrogram into it
             raise RuntimeError(f"spectrogram of shape {tuple(s.shape[2:])} does not fit size={tuple(self.size)}")

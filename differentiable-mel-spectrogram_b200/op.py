@@ -100,7 +100,6 @@ class _on_device:
 # the backward instead (cheaper forwards when most of them are never back-propagated, e.g. long validation loops).
 USE_JVP = os.environ.get("DMEL_NO_JVP", "0") != "1"
 
-_ws_bytes_cache: dict = {}
 _Y_SUM_OFFSET = [-1]
 
 
@@ -115,17 +114,12 @@ class DmelFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x: torch.Tensor, lambd: torch.Tensor, geo: Geometry, bank: Optional[DeviceBank],
+    def forward(ctx, x: torch.Tensor, lambd: torch.Tensor, ws: torch.Tensor, geo: Geometry, bank: Optional[DeviceBank],
                 log_eps: float, flags: int, lam_value: float):
         lib = _lib.load()
         dev = x.device
         shape = (geo.batch, 1, geo.n_frames, geo.rows) if (flags & _lib.FLAG_TIME_MAJOR) else (geo.batch, 1, geo.rows, geo.n_frames)
         y = torch.empty(shape, dtype=torch.float32, device=dev)
-        wkey = (geo.batch, geo.n_fft)
-        ws_bytes = _ws_bytes_cache.get(wkey)
-        if ws_bytes is None:
-            ws_bytes = _ws_bytes_cache[wkey] = lib.dmel_workspace_bytes(geo.batch, geo.n_fft)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         # The reference's training case: x is data, only lambd trains (models.py:19, main.py:27).  Then dy/dlambda is
         # produced by the forward itself (derivative-window STFT) and the backward is a dot product.
         jvp = (USE_JVP and ctx.needs_input_grad[1] and not ctx.needs_input_grad[0] and bool(lib.dmel_jvp_supported(geo.n_fft)))
@@ -135,15 +129,16 @@ class DmelFunction(torch.autograd.Function):
             if jvp:
                 rc = lib.dmel_forward_jvp_f32(
                     x.data_ptr(), geo.batch, geo.n_points, x.stride(0), lam_value, geo.win_length, geo.n_fft, geo.hop,
-                    geo.n_mels, bank_ref, float(log_eps), int(flags), y.data_ptr(), dy.data_ptr(),
-                    ws.data_ptr(), ws_bytes, _stream_ptr(dev))
+                    geo.n_mels, bank_ref, log_eps, flags, y.data_ptr(), dy.data_ptr(),
+                    ws.data_ptr(), ws.numel(), _stream_ptr(dev))
             else:
                 rc = lib.dmel_forward_f32(
                     x.data_ptr(), geo.batch, geo.n_points, x.stride(0), lam_value, geo.win_length, geo.n_fft, geo.hop,
-                    geo.n_mels, bank_ref, float(log_eps), int(flags), y.data_ptr(),
-                    ws.data_ptr(), ws_bytes, _stream_ptr(dev))
-        _lib.check(rc, "dmel_forward_jvp_f32" if jvp else "dmel_forward_f32")
-        ctx.geo, ctx.bank, ctx.log_eps, ctx.flags, ctx.lam_value = geo, bank, float(log_eps), int(flags), lam_value
+                    geo.n_mels, bank_ref, log_eps, flags, y.data_ptr(),
+                    ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        if rc:
+            _lib.check(rc, "dmel_forward_jvp_f32" if jvp else "dmel_forward_f32")
+        ctx.geo, ctx.bank, ctx.log_eps, ctx.flags, ctx.lam_value = geo, bank, log_eps, flags, lam_value
         ctx.ws = ws
         ctx.jvp = jvp
         ctx.lambd_shape, ctx.lambd_dtype = lambd.shape, lambd.dtype
@@ -153,57 +148,68 @@ class DmelFunction(torch.autograd.Function):
             ctx.save_for_backward(x, y)
         else:
             ctx.save_for_backward(x)
-        # fused by-product: sum of all outputs, one fp64 living in the workspace header (no extra launch)
-        off = _Y_SUM_OFFSET[0]
-        if off < 0:
-            off = _Y_SUM_OFFSET[0] = lib.dmel_workspace_y_sum_offset()
-        energy = ws[off:off + 8].view(torch.float64)[0]
-        ctx.mark_non_differentiable(energy)
-        return y, energy
+        return y
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, grad_y: torch.Tensor, _grad_energy=None):
+    def backward(ctx, grad_y: torch.Tensor):
         lib = _lib.load()
         geo = ctx.geo
         saved = ctx.saved_tensors
-        gy = grad_y.to(torch.float32).contiguous()
+        gy = grad_y
+        if gy.dtype != torch.float32 or not gy.is_contiguous():
+            gy = gy.to(torch.float32).contiguous()
         ws = ctx.ws
+        dev = gy.device
+        grad_lambda = torch.empty((), dtype=torch.float32, device=dev)
+        grad_x = None
         if ctx.jvp:
             dy = saved[0]
-            dev = dy.device
-            grad_lambda = torch.empty((), dtype=torch.float32, device=dev)
             with _on_device(dev):
                 rc = lib.dmel_lambda_grad_f32(gy.data_ptr(), dy.data_ptr(), gy.numel(), ctx.lam_value, grad_lambda.data_ptr(),
                                               ws.data_ptr(), ws.numel(), _stream_ptr(dev))
-            _lib.check(rc, "dmel_lambda_grad_f32")
-            return None, grad_lambda.reshape(ctx.lambd_shape).to(ctx.lambd_dtype), None, None, None, None, None
-        x = saved[0]
-        y = saved[1] if ctx.log_eps >= 0 else None
-        dev = x.device
-        need_dx = ctx.needs_input_grad[0]
-        grad_x = torch.empty((geo.batch, geo.n_points), dtype=torch.float32, device=dev) if need_dx else None
-        grad_lambda = torch.empty((), dtype=torch.float32, device=dev)
-        with _on_device(dev):
-            rc = lib.dmel_backward_f32(
-                x.data_ptr(), geo.batch, geo.n_points, x.stride(0),
-                ctx.lam_value, geo.win_length, geo.n_fft, geo.hop,
-                geo.n_mels, ctx.bank.ref() if ctx.bank is not None else None, ctx.log_eps,
-                ctx.flags, y.data_ptr() if y is not None else None, gy.data_ptr(),
-                grad_x.data_ptr() if need_dx else None, grad_lambda.data_ptr(),
-                ws.data_ptr(), ws.numel(), 1, _stream_ptr(dev))
-        _lib.check(rc, "dmel_backward_f32")
+            if rc:
+                _lib.check(rc, "dmel_lambda_grad_f32")
+        else:
+            x = saved[0]
+            y_ptr = saved[1].data_ptr() if ctx.log_eps >= 0 else None
+            need_dx = ctx.needs_input_grad[0]
+            if need_dx:
+                grad_x = torch.empty((geo.batch, geo.n_points), dtype=torch.float32, device=dev)
+            with _on_device(dev):
+                rc = lib.dmel_backward_f32(
+                    x.data_ptr(), geo.batch, geo.n_points, x.stride(0),
+                    ctx.lam_value, geo.win_length, geo.n_fft, geo.hop,
+                    geo.n_mels, ctx.bank.ref() if ctx.bank is not None else None, ctx.log_eps,
+                    ctx.flags, y_ptr, gy.data_ptr(),
+                    grad_x.data_ptr() if need_dx else None, grad_lambda.data_ptr(),
+                    ws.data_ptr(), ws.numel(), 1, _stream_ptr(dev))
+            if rc:
+                _lib.check(rc, "dmel_backward_f32")
         g_lambd = None
         if ctx.needs_input_grad[1]:
-            g_lambd = grad_lambda.reshape(ctx.lambd_shape).to(ctx.lambd_dtype)
-        return grad_x, g_lambd, None, None, None, None, None
+            g_lambd = grad_lambda
+            if ctx.lambd_shape != g_lambd.shape:
+                g_lambd = g_lambd.reshape(ctx.lambd_shape)
+            if ctx.lambd_dtype != torch.float32:
+                g_lambd = g_lambd.to(ctx.lambd_dtype)
+        return grad_x, g_lambd, None, None, None, None, None, None
+
+
+def workspace_energy(ws: torch.Tensor) -> torch.Tensor:
+    """0-d fp64 view of the fused by-product the forward leaves in its workspace header: the sum of all outputs
+    (what train.py:58 copies the whole spectrogram batch to the host for).  No launch, no copy."""
+    off = _Y_SUM_OFFSET[0]
+    if off < 0:
+        off = _Y_SUM_OFFSET[0] = _lib.load().dmel_workspace_y_sum_offset()
+    return ws[off:off + 8].view(torch.float64)[0]
 
 
 def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bool,
          normalize_window: bool = False, n_mels: int = 0, sample_rate: int = 0, f_min: float = 0.0,
          f_max: Optional[float] = None, log_eps: Optional[float] = None, remove_mean: bool = True,
          lambd_value: Optional[float] = None, return_energy: bool = False, time_major: bool = False,
-         out_affine: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+         out_affine: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, return_workspace: bool = False):
     """Functional form of both layers.
 
     x: (B, N) CUDA tensor (fp32; fp64/fp16 inputs are cast to fp32 — the reference's fp64
@@ -218,6 +224,8 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
     `out_affine=(scale, shift)` (two vectors of n_mels values, mel mode only) folds y <- scale[m]*y + shift[m] into the
     kernel epilogue, after the log: the eval-mode BatchNorm2d over mel bins that Cnn6 applies first (panns.py:169-172).
     The pair is a constant of the call (no gradient flows to it); gradients to x and lambd pass through it.
+    `return_workspace=True` returns `(y, ws)` instead, ws the call's workspace tensor (`workspace_energy(ws)` is the
+    energy; the layers keep it and build that view only when `last_energy` is read).
     """
     if x.dim() != 2:
         raise ValueError(f"expected x of shape (batch, n_points), got {tuple(x.shape)}")
@@ -254,11 +262,11 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
         if time_major and not lib.dmel_jvp_supported(geo.n_fft):
             raise _lib.DmelError(f"time_major output is implemented for n_fft 128..4096, got {geo.n_fft}")
         eps = -1.0 if log_eps is None else float(log_eps)
-        plan = (geo, bank, eps, flags)
+        plan = (geo, bank, eps, flags, int(lib.dmel_workspace_bytes(geo.batch, geo.n_fft)))
         if len(_plan_cache) > 64:
             _plan_cache.clear()
         _plan_cache[key] = plan
-    geo, bank, eps, flags = plan
+    geo, bank, eps, flags, ws_bytes = plan
     if out_affine is not None:
         if bank is None:
             raise ValueError("out_affine needs n_mels > 0 (it is a per-mel map)")
@@ -273,8 +281,11 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
                     _affine_cache.clear()
                 _affine_cache[akey] = abank
         bank = abank
-    y, energy = DmelFunction.apply(x, lambd, geo, bank, eps, flags, lam_value)
-    return (y, energy) if return_energy else y
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    y = DmelFunction.apply(x, lambd, ws, geo, bank, eps, flags, lam_value)
+    if return_workspace:
+        return y, ws
+    return (y, workspace_energy(ws)) if return_energy else y
 
 
 _plan_cache: dict = {}

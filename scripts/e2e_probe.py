@@ -43,3 +43,33 @@ pr = cProfile.Profile(); pr.enable()
 for i in range(200): step()
 pr.disable(); sync()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+
+# 4. H2D of one clip batch: one copy on one stream vs two half copies on two streams (two copy engines)
+s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+hx2 = [torch.randn(B, N).pin_memory() for _ in range(3)]
+half = B // 2
+def copy_one(i):
+    with torch.cuda.stream(s1):
+        dx_.copy_(hx2[i % 3], non_blocking=True)
+def copy_split(i):
+    h = hx2[i % 3]
+    with torch.cuda.stream(s1):
+        dx_[:half].copy_(h[:half], non_blocking=True)
+    with torch.cuda.stream(s2):
+        dx_[half:].copy_(h[half:], non_blocking=True)
+def copy_alt(i):
+    with torch.cuda.stream(s1 if i % 2 == 0 else s2):
+        dx_.copy_(hx2[i % 3], non_blocking=True)
+for name, fn in (("one stream", copy_one), ("two halves on two streams", copy_split), ("alternating streams", copy_alt)):
+    for i in range(10): fn(i)
+    sync(); t = time.perf_counter()
+    for i in range(300): fn(i)
+    sync(); dt = (time.perf_counter() - t) / 300
+    print(f"H2D 8.2 MB, {name}: {dt*1e6:.1f} us/batch = {B*N*4/dt/1e9:.1f} GB/s")
+for mb in (1, 4, 16, 64):
+    hb = torch.empty(mb * 2**20 // 4).pin_memory(); db = torch.empty_like(hb, device=dev)
+    for _ in range(5): db.copy_(hb, non_blocking=True)
+    sync(); t = time.perf_counter()
+    for _ in range(100): db.copy_(hb, non_blocking=True)
+    sync(); dt = (time.perf_counter() - t) / 100
+    print(f"H2D {mb} MiB back-to-back: {dt*1e6:.1f} us = {mb*2**20/dt/1e9:.1f} GB/s")
