@@ -265,31 +265,66 @@ static int check_launch(const char* what) {
     return DMEL_OK;
 }
 
+// Per-kernel launch state that does not change between calls: the opt-in to > 48 KB of dynamic shared memory and the
+// occupancy behind the persistent grid.  Both are properties of (kernel, device); they are looked up once per kernel
+// instantiation and device instead of on every launch (the host cost of a call is two launches' worth of driver work).
+constexpr int MAX_DEVICES = 64;
+struct KernelCache {
+    std::atomic<size_t> smem_ok[MAX_DEVICES];     // largest dynamic shared memory size already opted in
+    std::atomic<uint64_t> occ[MAX_DEVICES];       // (threads << 40 | smem << 8 | per_sm) of the last occupancy query
+    std::atomic<int> sms[MAX_DEVICES];
+};
+
+static int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        dev = 0;
+    }
+    return dev;
+}
+
 template <typename K>
-static int set_smem(K kernel, size_t smem) {
+static int set_smem(K kernel, size_t smem, KernelCache* kc = nullptr) {
     if (smem > 48 * 1024) {
+        const int dev = current_device();
+        if (kc && dev < MAX_DEVICES && kc->smem_ok[dev].load(std::memory_order_relaxed) >= smem) return DMEL_OK;
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) {
             fprintf(stderr, "[dmel] cudaFuncSetAttribute(%zu): %s\n", smem, cudaGetErrorString(e));
             (void)cudaGetLastError();
             return DMEL_ERR_LAUNCH_FAILED;
         }
+        if (kc && dev < MAX_DEVICES) kc->smem_ok[dev].store(smem, std::memory_order_relaxed);
     }
     return DMEL_OK;
 }
 
 // persistent launch: one resident wave of CTAs (occupancy x SM count), each walking tiles with stride gridDim
 template <typename K>
-static unsigned persistent_grid(K kernel, const LaunchPlan& lp, int64_t total_tiles) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, lp.threads, lp.smem) != cudaSuccess || per_sm < 1) {
-        (void)cudaGetLastError();
-        per_sm = 1;
+static unsigned persistent_grid(K kernel, const LaunchPlan& lp, int64_t total_tiles, KernelCache* kc = nullptr) {
+    const int dev = current_device();
+    const uint64_t key = (uint64_t(lp.threads) << 40) | (uint64_t(lp.smem) << 8);
+    int per_sm = 0, sms = 0;
+    if (kc && dev < MAX_DEVICES) {
+        const uint64_t c = kc->occ[dev].load(std::memory_order_relaxed);
+        if ((c & ~uint64_t(0xff)) == key && (c & 0xff) != 0) {
+            per_sm = int(c & 0xff);
+            sms = kc->sms[dev].load(std::memory_order_relaxed);
+        }
     }
-    int sms = NUM_SMS, dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) {
+    if (per_sm < 1 || sms < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, lp.threads, lp.smem) != cudaSuccess || per_sm < 1) {
+            (void)cudaGetLastError();
+            per_sm = 1;
+        }
+        sms = NUM_SMS;
         int v = 0;
         if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+        if (kc && dev < MAX_DEVICES) {
+            kc->sms[dev].store(sms, std::memory_order_relaxed);
+            kc->occ[dev].store(key | uint64_t(per_sm & 0xff), std::memory_order_relaxed);
+        }
     }
     const int64_t cap = int64_t(per_sm) * sms;
     return unsigned(std::min<int64_t>(total_tiles, cap));
@@ -298,9 +333,10 @@ static unsigned persistent_grid(K kernel, const LaunchPlan& lp, int64_t total_ti
 template <int L, int NG, bool SPEC, bool JVP>
 static int launch_fwd_t(const float* x, float* y, float* dy, const Geom& g, const MelDev& mel, const WsView& ws,
                         const LaunchPlan& lp, cudaStream_t st) {
+    static KernelCache kc;     // one per instantiation
     int rc;
-    if ((rc = set_smem(dmel_fwd_kernel<L, NG, SPEC, JVP>, lp.smem))) return rc;
-    const unsigned grid = persistent_grid(dmel_fwd_kernel<L, NG, SPEC, JVP>, lp, int64_t(g.B) * g.tiles_per_clip);
+    if ((rc = set_smem(dmel_fwd_kernel<L, NG, SPEC, JVP>, lp.smem, &kc))) return rc;
+    const unsigned grid = persistent_grid(dmel_fwd_kernel<L, NG, SPEC, JVP>, lp, int64_t(g.B) * g.tiles_per_clip, &kc);
     ProfScope prof(PROF_FWD, st);
     dmel_fwd_kernel<L, NG, SPEC, JVP><<<grid, lp.threads, lp.smem, st>>>(x, y, dy, g, mel, ws.win, ws.tw, ws.means, ws.hdr);
     return check_launch("dmel_fwd_kernel");
@@ -309,9 +345,10 @@ static int launch_fwd_t(const float* x, float* y, float* dy, const Geom& g, cons
 template <int L, int NG, bool SPEC, bool NEED_DX>
 static int launch_bwd_t(const float* x, const float* y, const float* gy, float* dx, const Geom& g, const MelDev& mel,
                         const WsView& ws, const LaunchPlan& lp, cudaStream_t st) {
+    static KernelCache kc;     // one per instantiation
     int rc;
-    if ((rc = set_smem(dmel_bwd_kernel<L, NG, SPEC, NEED_DX>, lp.smem))) return rc;
-    const unsigned grid = persistent_grid(dmel_bwd_kernel<L, NG, SPEC, NEED_DX>, lp, int64_t(g.B) * g.tiles_per_clip);
+    if ((rc = set_smem(dmel_bwd_kernel<L, NG, SPEC, NEED_DX>, lp.smem, &kc))) return rc;
+    const unsigned grid = persistent_grid(dmel_bwd_kernel<L, NG, SPEC, NEED_DX>, lp, int64_t(g.B) * g.tiles_per_clip, &kc);
     ProfScope prof(PROF_BWD, st);
     dmel_bwd_kernel<L, NG, SPEC, NEED_DX>
         <<<grid, lp.threads, lp.smem, st>>>(x, y, gy, dx, g, mel, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);

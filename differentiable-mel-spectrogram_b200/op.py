@@ -103,6 +103,16 @@ USE_JVP = os.environ.get("DMEL_NO_JVP", "0") != "1"
 _Y_SUM_OFFSET = [-1]
 
 
+_jvp_ok: dict = {}
+
+
+def _jvp_supported(lib, n_fft: int) -> bool:
+    ok = _jvp_ok.get(n_fft)
+    if ok is None:
+        ok = _jvp_ok[n_fft] = bool(lib.dmel_jvp_supported(n_fft))
+    return ok
+
+
 class DmelFunction(torch.autograd.Function):
     """y = DMEL(x, lambd).
 
@@ -122,7 +132,7 @@ class DmelFunction(torch.autograd.Function):
         y = torch.empty(shape, dtype=torch.float32, device=dev)
         # The reference's training case: x is data, only lambd trains (models.py:19, main.py:27).  Then dy/dlambda is
         # produced by the forward itself (derivative-window STFT) and the backward is a dot product.
-        jvp = (USE_JVP and ctx.needs_input_grad[1] and not ctx.needs_input_grad[0] and bool(lib.dmel_jvp_supported(geo.n_fft)))
+        jvp = USE_JVP and ctx.needs_input_grad[1] and not ctx.needs_input_grad[0] and _jvp_supported(lib, geo.n_fft)
         dy = torch.empty_like(y) if jvp else None
         bank_ref = bank.ref() if bank is not None else None
         with _on_device(dev):
