@@ -222,3 +222,16 @@ def test_product_package_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("no oracle", ""), fn
+
+
+def test_missing_library_fails_loudly_instead_of_falling_back(monkeypatch, tmp_path):
+    """No CPU or PyTorch fallback exists: without libdmel_b200.so the product raises, it never computes another way."""
+    lib_mod = dm._lib
+    monkeypatch.setattr(lib_mod, "_lib", None)
+    monkeypatch.setattr(lib_mod, "LIB_PATH", str(tmp_path / "libdmel_b200.so"))
+    monkeypatch.delenv("DMEL_LIB_PATH", raising=False)
+    with pytest.raises(dm.DmelError, match="no CPU fallback|not found"):
+        lib_mod.load()
+    layer = dm.MelSpectrogramLayer(torch.tensor(20.0), n_mels=8, n_points=800, sample_rate=8000, hop_length=80, optimized=True)
+    with pytest.raises(dm.DmelError):
+        layer(torch.randn(2, 800))              # CPU tensors are refused as well
