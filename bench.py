@@ -414,6 +414,7 @@ def main():
     # ---- e2e through the public module from pinned host memory ----
     e2e = None
     ms_pcm = 0.0
+    ms_graph = 0.0
     if not args.no_e2e:
         layer = dm.MelSpectrogramLayer(torch.tensor(lam), n_mels=M, n_points=N, sample_rate=sr, hop_length=hop,
                                        device=str(dev), optimized=True, log_eps=LOG_EPS).to(dev)
@@ -495,6 +496,54 @@ def main():
         barrier()
         ms_pcm = ev0.elapsed_time(ev1)
 
+        # Extra: the same fp32 loop with the layer's forward+backward captured once per device buffer in a
+        # torch.cuda.CUDAGraph and replayed per step (supported use of the layer, tests/test_gpu_parity.py): what the
+        # end-to-end rate is once the ~150 us of Python / autograd per eager step are gone.  1 GPU only.
+        if world == 1:
+            try:
+                graphs, grads = [], []
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(main_stream)
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        step_f32(0)
+                main_stream.wait_stream(side)
+                for b in range(NB_E2E):
+                    layer.lambd.grad = None
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr):
+                        xin = xdev[b].detach().requires_grad_(True)
+                        layer(xin).backward(Gs[b % R])
+                    graphs.append(gr)
+                    grads.append(layer.lambd.grad)
+
+                def graph_loop(k):
+                    for i in range(k + 2):
+                        if i < k:
+                            cs = copy_streams[i % 2]
+                            with torch.cuda.stream(cs):
+                                cs.wait_event(free[i % NB_E2E])
+                                up_f32(i)
+                                ready[i % NB_E2E].record(cs)
+                        j = i - 2
+                        if j >= 0:
+                            main_stream.wait_event(ready[j % NB_E2E])
+                            graphs[j % NB_E2E].replay()
+                            free[j % NB_E2E].record(main_stream)
+                            host_slot[j % 2].copy_(grads[j % NB_E2E], non_blocking=True)
+
+                graph_loop(5)
+                torch.cuda.synchronize()
+                ev0.record()
+                graph_loop(e2e_steps)
+                ev1.record()
+                torch.cuda.synchronize()
+                ms_graph = ev0.elapsed_time(ev1)
+            except Exception as exc:   # an extra must never cost the bench line
+                print(f"[bench] e2e_graph skipped: {exc}", file=sys.stderr)
+                ms_graph = 0.0
+                torch.cuda.synchronize()
+
     clocks = sampler.stop() if sampler else None
 
     # max over ranks
@@ -549,6 +598,12 @@ def main():
             line["e2e"] = {"value": world * audio_s * e2e[1] / (e2e[0] * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": 4 * B * N, "d2h_bytes_per_step": 4, "steps": e2e[1],
                            "api": "MelSpectrogramLayer.forward + Tensor.backward (eager), pinned host x, uploads pipelined over two copy streams"}
+            if ms_graph > 0:
+                line["e2e_graph"] = {"value": world * audio_s * e2e[1] / (ms_graph * 1e-3), "unit": UNIT,
+                                     "h2d_bytes_per_step": 4 * B * N, "d2h_bytes_per_step": 4,
+                                     "note": "same loop, the layer's forward+backward captured in a torch.cuda.CUDAGraph "
+                                             "per device buffer and replayed (no Python/autograd per step); extra, not "
+                                             "the headline e2e"}
             line["e2e_pcm16"] = {"value": world * audio_s * e2e[1] / (ms_pcm * 1e-3), "unit": UNIT,
                                  "h2d_bytes_per_step": 2 * B * N, "d2h_bytes_per_step": 4,
                                  "note": "same loop with int16 PCM host clips (the datasets' native format), widened to fp32 on "
