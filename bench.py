@@ -7,13 +7,15 @@
 
 One "step" = one fused forward + one fused backward (dL/dx AND dL/dlambda, log fused, eps 1e-10) over one
 batch of synthetic clips of the named BASELINE.json shape; with N > 1 every rank runs the same per-GPU batch
-(weak scaling) and the step ends with the one collective of the path: an NCCL all-reduce of the scalar
-dL/dlambda.  Prints ONE JSON line (rank 0).
+(weak scaling) and the step ends with the one collective of the path: the all-reduce of the scalar dL/dlambda
+(fused into the backward over NVLink peer memory; --nccl-only uses NCCL).  Prints ONE JSON line (rank 0).
 
   value      whole-job audio-s/s, inputs resident in HBM, C-ABI calls replayed from a CUDA graph
              (the small shapes are launch-bound otherwise); buffers rotate over a set > 2x L2
   e2e        same metric through the public nn.Module (MelSpectrogramLayer.forward + .backward) from
              PINNED HOST clips: H2D of x every step and D2H of the step's scalar result inside the timed region
+             (extras, not the headline: e2e_pcm16 = int16 host clips; e2e_graph = the layer's step replayed from a
+             torch.cuda.CUDAGraph; lambda_only = steps where only lambd trains)
   roofline   dominant kernel: algorithmic bytes per launch / its mean CUDA-event duration, vs the measured
              HBM copy peak in MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle port of the reference path (oracle/dmel_oracle.py: per-sample loop, torch.stft,
