@@ -361,7 +361,12 @@ def main():
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    per_step_launches = 5   # prep + forward + zero-init + backward + finalize
+    # launches of OUR kernels per step, counted by the library itself (prep + forward + zero-init + backward, + finalize
+    # where it is not fused into the backward)
+    c0 = lib.dmel_launch_count(-1)
+    resident_step(0)
+    torch.cuda.synchronize(dev)
+    per_step_launches = int(lib.dmel_launch_count(-1) - c0)
     gpu_launches = per_step_launches * args.steps
 
     # per-kernel durations: same steps, eager, each main kernel bracketed by CUDA events on its stream
