@@ -13,10 +13,12 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmel_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
-ABI_VERSION = 2
+ABI_VERSION = 3
 FLAG_NORMALIZE_WINDOW = 1
 FLAG_KEEP_MEAN = 2
 FLAG_TIME_MAJOR = 4
+FLAG_X_I16 = 8
+FLAG_X_F16 = 16
 
 # every symbol include/dmel.h declares
 EXPORTED_SYMBOLS = (
@@ -29,6 +31,9 @@ EXPORTED_SYMBOLS = (
     "dmel_forward_f32",
     "dmel_forward_jvp_f32",
     "dmel_jvp_supported",
+    "dmel_x16_supported",
+    "dmel_segment_table_bytes",
+    "dmel_build_segment_tables",
     "dmel_lambda_grad_f32",
     "dmel_backward_f32",
     "dmel_backward_allreduce_f32",
@@ -62,6 +67,7 @@ class MelBankStruct(ctypes.Structure):
         ("bin_w", ctypes.c_void_p),
         ("out_scale", ctypes.c_void_p),
         ("out_shift", ctypes.c_void_p),
+        ("seg_tables", ctypes.c_void_p),
     ]
 
 
@@ -131,6 +137,13 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.dmel_forward_jvp_f32.argtypes = lib.dmel_forward_f32.argtypes[:13] + [c.c_void_p] + lib.dmel_forward_f32.argtypes[13:]
     lib.dmel_jvp_supported.restype = c.c_int
     lib.dmel_jvp_supported.argtypes = [c.c_int32]
+    lib.dmel_x16_supported.restype = c.c_int
+    lib.dmel_x16_supported.argtypes = [c.c_int32]
+    lib.dmel_segment_table_bytes.restype = c.c_size_t
+    lib.dmel_segment_table_bytes.argtypes = [c.c_int32]
+    lib.dmel_build_segment_tables.restype = c.c_int
+    lib.dmel_build_segment_tables.argtypes = [c.POINTER(MelBankStruct), c.c_int32, c.c_void_p, c.c_size_t, c.c_void_p,
+                                              c.POINTER(c.c_int32)]
     lib.dmel_lambda_grad_f32.restype = c.c_int
     lib.dmel_lambda_grad_f32.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_float, c.c_void_p, c.c_void_p, c.c_size_t,
                                          c.c_void_p]

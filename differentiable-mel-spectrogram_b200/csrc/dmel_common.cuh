@@ -27,6 +27,23 @@ struct WsHeader {
 };
 static_assert(sizeof(WsHeader) == 64, "header is 64 bytes");
 
+// Segment-owner form of the mel projection (second-generation forward).  Every bin k with a non-zero weight feeds the
+// mels m0(k) and m0(k)+1 (triangular bank: the bin-major form of dmel.h); the bins with the same m0 are one contiguous
+// *segment* s = m0.  Thread `s mod GT` of an FFT group owns segment s (pass s / GT): the split phase writes P[k] into
+// slot (base[pass] + j) * (GT+1) + (s mod GT), j the bin's position inside its segment, so that the owner afterwards
+// reads its bins — and their two weights from `w`, same indexing — at conflict-free consecutive-lane addresses:
+//   mel[s] = sum_j w[.].x * P[.]  (+)  mel[s+1] += sum_j w[.].y * P[.]
+// Built ONCE per (bank, n_fft) by dmel_build_segment_tables (dmel.h) into caller-owned device memory that the bank
+// struct points to (dmel_melbank.seg_tables); without it the forward falls back to the row gather.
+constexpr int SEG_MAX_PASSES = 8;
+struct SegHeader {
+    int32_t use_seg;                 // 0: bank is not of that shape / tables do not fit -> row-gather fallback
+    int32_t npass, nslot, pad_;
+    int32_t base[SEG_MAX_PASSES];    // first slot of each pass
+    int32_t maxlen[SEG_MAX_PASSES];  // longest segment of each pass
+};
+static_assert(sizeof(SegHeader) == 80, "SegHeader is 80 bytes");
+
 struct WsView {
     WsHeader* hdr;
     float* win;       // [n_fft]
@@ -34,6 +51,31 @@ struct WsView {
     float* means;     // [B]
     double* clipsum;  // [B]
 };
+
+// view of a segment-table blob: SegHeader | (w0, w1) per slot [seg_capacity] | slot of every bin [n_fft/2+1 (+pad)]
+// (bins without weights point at the dummy slot nslot*(GT+1))
+struct SegView {
+    SegHeader* hdr;   // nullptr: no tables
+    float2* w;
+    int32_t* dest;
+};
+
+// slots available for the segment tables: the P values share the group's FFT buffer (fft_core.cuh: padded(L) + 2)
+__host__ __device__ inline int seg_capacity(int n_fft) { return n_fft + (n_fft >> 4) + 2; }
+static inline size_t seg_blob_bytes(int n_fft) {
+    return 96 + ((size_t(seg_capacity(n_fft)) * 8 + 15) & ~size_t(15)) + ((size_t(n_fft / 2 + 4) * 4 + 15) & ~size_t(15));
+}
+static inline SegView seg_view(void* blob, int n_fft) {
+    SegView v{nullptr, nullptr, nullptr};
+    if (!blob) return v;
+    unsigned char* p = static_cast<unsigned char*>(blob);
+    v.hdr = reinterpret_cast<SegHeader*>(p);
+    p += 96;
+    v.w = reinterpret_cast<float2*>(p);
+    p += (size_t(seg_capacity(n_fft)) * 8 + 15) & ~size_t(15);
+    v.dest = reinterpret_cast<int32_t*>(p);
+    return v;
+}
 
 static inline size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 
@@ -69,6 +111,8 @@ struct Geom {
     int row_aligned;             // x and x_stride are 16-byte aligned: spans may move as 16-byte quads
     int lookahead;               // 1: span (and dL/dy, y) buffers are doubled and tile i+1 is prefetched during tile i
     int time_major;              // y / dL/dy / dy are (B,1,T,rows) instead of (B,1,rows,T)
+    int x_dtype;                 // DMEL_X_F32 / DMEL_X_I16 / DMEL_X_F16 (16-bit inputs: second-generation tiled kernels only;
+                                 // row_aligned then means 8-byte alignment of x and of the row stride)
 };
 
 struct MelDev {
@@ -80,6 +124,7 @@ struct MelDev {
     const float* bin_w;
     const float* out_scale;   // per-mel affine folded into the epilogue (dmel.h); both null = identity
     const float* out_shift;
+    SegView seg;              // segment tables of the bank (hdr == nullptr: none)
 };
 
 // Frames handled by each of the NG groups of a tile holding nfr (<= TT = NG*SF) frames.  Full tiles: SF.  The
@@ -193,6 +238,14 @@ __device__ __forceinline__ void span_issue(float* xs_sh, const float* __restrict
     const int shift = p0 & 3;                       // p0 may be negative: & 3 is still the mod-4 phase
     float* base = xs_sh;                            // storage word i + shift holds span index i
     const int nq = (span + shift + 3) >> 2;
+    if (row_aligned && p0 - shift >= 0 && p0 - shift + 4 * nq <= N) {
+        // interior tile: every quad is in range (the quads at both ends may carry up to 3 samples outside the span;
+        // they are inside the clip and nobody reads them)
+        const float4* src = reinterpret_cast<const float4*>(xb + (p0 - shift));
+        float4* dst = reinterpret_cast<float4*>(base);
+        for (int q = tid; q < nq; q += NT) cp_async16(dst + q, src + q);
+        return;
+    }
     for (int q = tid; q < nq; q += NT) {
         const int i0 = 4 * q - shift;               // span index of the quad's first word
         const int p = p0 + i0;                      // global sample index, multiple of 4 by construction
@@ -216,6 +269,15 @@ template <int NT>
 __device__ __forceinline__ void span_centre(float* xs_sh, int p0, int span, int N, float mu, int tid) {
     const int shift = p0 & 3;
     const int nq = (span + shift + 3) >> 2;
+    if (p0 - shift >= 0 && p0 - shift + 4 * nq <= N) {   // interior tile (same test as span_issue: same words per thread)
+        float4* d4 = reinterpret_cast<float4*>(xs_sh);
+        for (int q = tid; q < nq; q += NT) {
+            float4 v = d4[q];
+            v.x -= mu; v.y -= mu; v.z -= mu; v.w -= mu;
+            d4[q] = v;
+        }
+        return;
+    }
     for (int q = tid; q < nq; q += NT) {
         const int i0 = 4 * q - shift;
         const int p = p0 + i0;

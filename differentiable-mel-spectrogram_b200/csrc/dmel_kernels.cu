@@ -50,6 +50,7 @@
 #include "dmel_common.cuh"
 #include "dmel_small_kernels.cuh"
 #include "dmel_tiled_kernels.cuh"
+#include "dmel_tiled2_kernels.cuh"
 #include "dmel_big_kernels.cuh"
 #include "dmel_dft_kernels.cuh"
 
@@ -102,13 +103,67 @@ static FftInfo fft_info(int n_fft) {
 
 static bool has_fft_plan(int n_fft) { return fft_info(n_fft).ok; }
 
+// second-generation tiled kernels (fft_core.cuh / dmel_tiled2_kernels.cuh): n_fft 256..4096, 16 points per thread.
+// DMEL_V1=1 in the environment keeps the first generation (A/B measurements).
+template <int L> static PlanDesc plan2_desc_of() {
+    PlanDesc d;
+    d.np = v2::Fft<L>::NP;
+    d.r[0] = 16; d.r[1] = v2::Fft<L>::R1; d.r[2] = v2::Fft<L>::R2; d.r[3] = 1;
+    return d;
+}
+struct Fft2Info {
+    bool ok;
+    int gt, tw_smem, buf;
+    int ng[2];
+    PlanDesc desc;
+};
+static Fft2Info fft2_info(int n_fft) {
+    Fft2Info f{};
+    static const bool v1 = getenv("DMEL_V1") != nullptr && atoi(getenv("DMEL_V1")) != 0;
+    if (v1) return f;
+    switch (n_fft) {
+#define DMEL_FFT2_CASE(LL, NGA, NGB)                                                                             \
+    case LL: f.ok = true; f.gt = v2::Fft<LL>::GT; f.tw_smem = v2::Fft<LL>::TW_SMEM; f.buf = v2::Fft<LL>::BUF;      \
+             f.ng[0] = NGA; f.ng[1] = NGB; f.desc = plan2_desc_of<LL>(); break;
+        DMEL_FFT2_CASE(256, 8, 4)
+        DMEL_FFT2_CASE(512, 8, 4)
+        DMEL_FFT2_CASE(1024, 4, 2)
+        DMEL_FFT2_CASE(2048, 2, 1)
+        DMEL_FFT2_CASE(4096, 1, 1)
+#undef DMEL_FFT2_CASE
+        default: break;
+    }
+    return f;
+}
+
 struct LaunchPlan {
     int path;  // 0 FFT, 1 direct DFT, 2 big FFT
+    int gen;   // tiled FFT path: 1 first-generation kernels, 2 second generation
     int lookahead;
     int NG, SF, TT, span, sub_span, tiles_per_clip, threads;
     int csr_ints, csr_floats;
     size_t smem;
 };
+
+// second generation: forward keeps an [M][TT+1] tile (two planes for the JVP forward) and int2-per-mel records + the
+// mel-major weights; backward keeps (M+1) x (TT+2) tiles of dL/dy and y (doubled by the look-ahead) and one 16-byte
+// record per bin
+static size_t smem_bytes_fft2(const Fft2Info& fi, int NG, int span, int sub_span, int M, int F, int TT, int mel_nnz,
+                              bool spec, bool bwd, bool priv_dx, int lookahead, bool jvp, bool seg) {
+    const int n_fft = 2 * (F - 1);
+    int tile_words, meta_words, w_words;
+    if (bwd) {
+        tile_words = (2 + 2 * lookahead) * round_up4((M + 1) * (TT + 2));
+        meta_words = spec ? 0 : 4 * F;
+        w_words = 0;
+    } else {
+        tile_words = jvp ? 2 * round_up4(M * (TT + 1)) : M * (TT + 1);
+        meta_words = spec ? 0 : 2 * M;
+        w_words = spec ? 0 : (seg ? v2::fwd_weight_words(n_fft, mel_nnz) : mel_nnz);
+    }
+    return size_t(v2::make_lay2(fi.tw_smem, fi.buf, NG, span, sub_span, tile_words, meta_words, w_words, priv_dx,
+                                1 + lookahead).total) * 4;
+}
 
 static size_t smem_bytes_fft(int L, int NG, int tw_total, int span, int sub_span, int M, int TT, int csr_ints,
                              int csr_floats, bool bwd, bool priv_dx, int lookahead, bool jvp = false) {
@@ -126,7 +181,7 @@ static size_t smem_bytes_fft(int L, int NG, int tw_total, int span, int sub_span
 // until the tile fits shared memory or the clip.
 // DMEL_NG / DMEL_SF in the environment pin the choice (tuning experiments).
 static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int csr_ints, int csr_floats, bool bwd,
-                       bool need_dx, LaunchPlan* lp, bool jvp = false) {
+                       bool need_dx, LaunchPlan* lp, bool jvp = false, bool seg = false) {
     (void)B;
     const int64_t T64 = N / hop + 1;
     if (T64 > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
@@ -166,21 +221,30 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
         }
         return DMEL_ERR_SMEM_EXCEEDED;
     }
+    const Fft2Info f2 = fft2_info(n_fft);
+    const bool spec_mode = csr_floats == 0;
+    lp->gen = f2.ok ? 2 : 1;
     int pin_ng = 0, pin_sf = 0;
     if (const char* e = getenv("DMEL_NG")) pin_ng = atoi(e);
     if (const char* e = getenv("DMEL_SF")) pin_sf = atoi(e);
     // measured optima (scripts/tune.py on B200, profiles/*tune*.log): (groups, frames per group)
     int ng_pref, sf_pref;
     switch (n_fft) {
-        case 1024: ng_pref = (bwd && need_dx) ? 4 : 2; sf_pref = (bwd && need_dx) ? 4 : 8; break;
-        case 2048: ng_pref = 1; sf_pref = 8; break;
+        case 1024:
+            if (f2.ok) { ng_pref = 2; sf_pref = (bwd && !need_dx) ? 4 : 8; }   // r02h sweep (profiles/)
+            else { ng_pref = (bwd && need_dx) ? 4 : 2; sf_pref = (bwd && need_dx) ? 4 : 8; }
+            break;
+        case 2048: ng_pref = 1; sf_pref = (f2.ok && !bwd && !jvp) ? 4 : 8; break;
         case 4096: ng_pref = 1; sf_pref = 32; break;
+        case 256: ng_pref = f2.ok ? 8 : 4; sf_pref = f2.ok ? 2 : 4; break;   // gen 2: half a warp per transform
         default: ng_pref = 4; sf_pref = 4; break;    // one warp per transform
     }
+    const int gt = f2.ok ? f2.gt : fi.gt;
+    const int* ngs = f2.ok ? f2.ng : fi.ng;
     for (int attempt = 0; attempt < 2; ++attempt) {
         for (int ni = 0; ni < 2; ++ni) {
             // first the preferred NG, then the other instantiated one
-            const int NG = (ni == 0) ? ng_pref : (fi.ng[0] == ng_pref ? fi.ng[1] : fi.ng[0]);
+            const int NG = (ni == 0) ? ng_pref : (ngs[0] == ng_pref ? ngs[1] : ngs[0]);
             if (ni == 1 && NG == ng_pref) continue;
             if (pin_ng && NG != pin_ng) continue;
             int sf0 = pin_sf ? pin_sf : sf_pref;
@@ -190,14 +254,19 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
                 const int tt = NG * SF;
                 const int64_t span64 = int64_t(tt - 1) * hop + n_fft, sub64 = int64_t(SF - 1) * hop + n_fft;
                 if (span64 <= (1 << 20)) {
-                    size_t sm = smem_bytes_fft(n_fft, NG, fi.tw_total, int(span64), int(sub64), rows, tt, csr_ints, csr_floats,
-                                               bwd, bwd && need_dx, 0, jvp);
+                    auto smem_of = [&](int la) {
+                        return f2.ok ? smem_bytes_fft2(f2, NG, int(span64), int(sub64), rows, n_fft / 2 + 1, tt, csr_floats,
+                                                       spec_mode, bwd, bwd && need_dx, la, jvp, seg)
+                                     : smem_bytes_fft(n_fft, NG, fi.tw_total, int(span64), int(sub64), rows, tt, csr_ints,
+                                                      csr_floats, bwd, bwd && need_dx, la, jvp);
+                    };
+                    size_t sm = smem_of(0);
                     if (sm <= SMEM_MAX) {
                         // one-tile look-ahead (double buffers) only if it does not cost a resident CTA
-                        const size_t sm2 = smem_bytes_fft(n_fft, NG, fi.tw_total, int(span64), int(sub64), rows, tt, csr_ints,
-                                                          csr_floats, bwd, bwd && need_dx, 1, jvp);
-                        const int warps_cta = NG * fi.gt / 32;
-                        const int reg_cap = std::max(1, (n_fft <= 512 && NG == 4 && !(bwd && need_dx) ? 20 : 16) / warps_cta);
+                        const size_t sm2 = smem_of(1);
+                        const int warps_cta = std::max(1, NG * gt / 32);
+                        const bool cap96 = f2.ok ? (n_fft <= 512 && !bwd && !jvp) : (n_fft <= 512 && NG == 4 && !(bwd && need_dx));
+                        const int reg_cap = std::max(1, (cap96 ? 20 : 16) / warps_cta);
                         auto ctas = [&](size_t b) { return std::min<int>(reg_cap, int(SMEM_MAX / (b + 1024))); };
                         lp->lookahead = 0;
                         if (!getenv("DMEL_NO_LOOKAHEAD") && sm2 <= SMEM_MAX && ctas(sm2) >= ctas(sm)) {
@@ -209,7 +278,7 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
                         lp->NG = NG; lp->SF = SF; lp->TT = tt;
                         lp->span = int(span64); lp->sub_span = int(sub64);
                         lp->tiles_per_clip = (T + tt - 1) / tt;
-                        lp->threads = NG * fi.gt;
+                        lp->threads = NG * gt;
                         lp->smem = sm;
                         return DMEL_OK;
                     }
@@ -377,6 +446,80 @@ static int launch_bwd(const float* x, const float* y, const float* gy, float* dx
               : launch_bwd_t<L, NG, false, false>(x, y, gy, dx, g, mel, ws, lp, st);
 }
 
+// ---- second generation
+template <int L, int NG, bool SPEC, bool JVP>
+static int launch_fwd2_t(const void* x, float* y, float* dy, const Geom& g, const MelDev& mel, const WsView& ws,
+                         const LaunchPlan& lp, cudaStream_t st) {
+    static KernelCache kc;     // one per instantiation
+    int rc;
+    if ((rc = set_smem(v2::dmel2_fwd_kernel<L, NG, SPEC, JVP>, lp.smem, &kc))) return rc;
+    const unsigned grid = persistent_grid(v2::dmel2_fwd_kernel<L, NG, SPEC, JVP>, lp, int64_t(g.B) * g.tiles_per_clip, &kc);
+    ProfScope prof(PROF_FWD, st);
+    v2::dmel2_fwd_kernel<L, NG, SPEC, JVP><<<grid, lp.threads, lp.smem, st>>>(x, y, dy, g, mel, ws.win, ws.tw, ws.means, ws.hdr);
+    return check_launch("dmel2_fwd_kernel");
+}
+
+template <int L, int NG, bool SPEC, bool NEED_DX>
+static int launch_bwd2_t(const void* x, const float* y, const float* gy, float* dx, const Geom& g, const MelDev& mel,
+                         const WsView& ws, const LaunchPlan& lp, cudaStream_t st) {
+    static KernelCache kc;     // one per instantiation
+    int rc;
+    if ((rc = set_smem(v2::dmel2_bwd_kernel<L, NG, SPEC, NEED_DX>, lp.smem, &kc))) return rc;
+    const unsigned grid = persistent_grid(v2::dmel2_bwd_kernel<L, NG, SPEC, NEED_DX>, lp, int64_t(g.B) * g.tiles_per_clip, &kc);
+    ProfScope prof(PROF_BWD, st);
+    v2::dmel2_bwd_kernel<L, NG, SPEC, NEED_DX>
+        <<<grid, lp.threads, lp.smem, st>>>(x, y, gy, dx, g, mel, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
+    return check_launch("dmel2_bwd_kernel");
+}
+
+template <int L, int NG>
+static int launch_fwd2(const void* x, float* y, float* dy, const Geom& g, const MelDev& mel, bool spec, const WsView& ws,
+                       const LaunchPlan& lp, cudaStream_t st) {
+    if (dy) {
+        return spec ? launch_fwd2_t<L, NG, true, true>(x, y, dy, g, mel, ws, lp, st)
+                    : launch_fwd2_t<L, NG, false, true>(x, y, dy, g, mel, ws, lp, st);
+    }
+    return spec ? launch_fwd2_t<L, NG, true, false>(x, y, nullptr, g, mel, ws, lp, st)
+                : launch_fwd2_t<L, NG, false, false>(x, y, nullptr, g, mel, ws, lp, st);
+}
+
+template <int L, int NG>
+static int launch_bwd2(const void* x, const float* y, const float* gy, float* dx, const Geom& g, const MelDev& mel,
+                       bool spec, const WsView& ws, const LaunchPlan& lp, cudaStream_t st) {
+    if (spec) {
+        return dx ? launch_bwd2_t<L, NG, true, true>(x, y, gy, dx, g, mel, ws, lp, st)
+                  : launch_bwd2_t<L, NG, true, false>(x, y, gy, dx, g, mel, ws, lp, st);
+    }
+    return dx ? launch_bwd2_t<L, NG, false, true>(x, y, gy, dx, g, mel, ws, lp, st)
+              : launch_bwd2_t<L, NG, false, false>(x, y, gy, dx, g, mel, ws, lp, st);
+}
+
+#ifdef DMEL_FAST_BUILD
+// development builds: only the shapes of the benchmarked workloads (seconds instead of minutes to compile)
+#define DMEL_DISPATCH2(n_fft, ng, CALL)                                  \
+    switch ((n_fft) * 16 + (ng)) {                                       \
+        case 512 * 16 + 4: rc = CALL(512, 4); break;                     \
+        case 1024 * 16 + 4: rc = CALL(1024, 4); break;                   \
+        case 1024 * 16 + 2: rc = CALL(1024, 2); break;                   \
+        case 2048 * 16 + 1: rc = CALL(2048, 1); break;                   \
+        default: rc = DMEL_ERR_UNSUPPORTED_NFFT;                         \
+    }
+#else
+#define DMEL_DISPATCH2(n_fft, ng, CALL)                                  \
+    switch ((n_fft) * 16 + (ng)) {                                       \
+        case 256 * 16 + 8: rc = CALL(256, 8); break;                     \
+        case 256 * 16 + 4: rc = CALL(256, 4); break;                     \
+        case 512 * 16 + 8: rc = CALL(512, 8); break;                     \
+        case 512 * 16 + 4: rc = CALL(512, 4); break;                     \
+        case 1024 * 16 + 4: rc = CALL(1024, 4); break;                   \
+        case 1024 * 16 + 2: rc = CALL(1024, 2); break;                   \
+        case 2048 * 16 + 2: rc = CALL(2048, 2); break;                   \
+        case 2048 * 16 + 1: rc = CALL(2048, 1); break;                   \
+        case 4096 * 16 + 1: rc = CALL(4096, 1); break;                   \
+        default: rc = DMEL_ERR_UNSUPPORTED_NFFT;                         \
+    }
+#endif
+
 template <int L>
 static int launch_big_fwd(const float* x, float* y, const Geom& g, const MelDev& mel, bool spec, const WsView& ws,
                           const LaunchPlan& lp, cudaStream_t st) {
@@ -417,6 +560,9 @@ static int launch_big_bwd(const float* x, const float* y, const float* gy, float
 }
 
 // (n_fft, NG) -> instantiation; the NG values must match fft_info()
+#ifdef DMEL_FAST_BUILD
+#define DMEL_DISPATCH(n_fft, ng, CALL) rc = DMEL_ERR_UNSUPPORTED_NFFT;
+#else
 #define DMEL_DISPATCH(n_fft, ng, CALL)                                   \
     switch ((n_fft) * 16 + (ng)) {                                       \
         case 128 * 16 + 8: rc = CALL(128, 8); break;                     \
@@ -432,8 +578,9 @@ static int launch_big_bwd(const float* x, const float* y, const float* gy, float
         case 4096 * 16 + 1: rc = CALL(4096, 1); break;                   \
         default: rc = DMEL_ERR_UNSUPPORTED_NFFT;                         \
     }
+#endif
 
-static int validate(const float* x, int64_t B, int64_t N, int64_t stride, int32_t win, int32_t n_fft, int32_t hop,
+static int validate(const void* x, int64_t B, int64_t N, int64_t stride, int32_t win, int32_t n_fft, int32_t hop,
                     int32_t n_mels, const dmel_melbank* bank, void* ws, size_t ws_bytes_in) {
     if (!x || !ws) return DMEL_ERR_NULL_POINTER;
     if (B <= 0 || N <= 0 || hop <= 0 || win <= 0 || n_fft < win || n_mels < 0 || stride < N) return DMEL_ERR_BAD_GEOMETRY;
@@ -461,12 +608,13 @@ static MelDev mel_dev(const dmel_melbank* bank) {
         m.mel_k0 = bank->mel_k0; m.mel_off = bank->mel_off; m.mel_w = bank->mel_w;
         m.bin_m0 = bank->bin_m0; m.bin_off = bank->bin_off; m.bin_w = bank->bin_w;
         m.out_scale = bank->out_scale; m.out_shift = bank->out_shift;
+        m.seg = seg_view(const_cast<void*>(bank->seg_tables), 2 * (bank->n_freqs - 1));
     }
     return m;
 }
 
-static int run_prep(const float* x, int64_t B, int64_t N, int64_t stride, float lam_abs, int32_t win, int32_t n_fft,
-                    int32_t flags, const WsView& ws, cudaStream_t st) {
+static int run_prep(const void* x, int64_t B, int64_t N, int64_t stride, float lam_abs, int32_t win, int32_t n_fft,
+                    int32_t flags, const WsView& ws, cudaStream_t st, bool gen2) {
     ProfScope prof(PROF_PREP, st);
     const int nseg = prep_segments(int(N));
     if ((B + 1) * int64_t(nseg) > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
@@ -481,7 +629,7 @@ static int run_prep(const float* x, int64_t B, int64_t N, int64_t stride, float 
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, dmel_prep_kernel, x, (long long)stride, int(B), int(N), lam_abs, int(win), int(n_fft),
-                       int(flags), ws, fft_info(n_fft).desc);
+                       int(flags), ws, gen2 ? fft2_info(n_fft).desc : fft_info(n_fft).desc);
     return check_launch("dmel_prep_kernel");
 }
 
@@ -570,10 +718,26 @@ static Geom make_geom(int64_t B, int64_t N, int64_t stride, int32_t n_fft, int32
     g.row_aligned = 0;
     g.lookahead = lp.lookahead;
     g.time_major = 0;
+    g.x_dtype = DMEL_X_F32;
     return g;
 }
 
-static int forward_impl(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
+// sample type of x from the call flags; 16-bit inputs need the second-generation tiled kernels
+static int x_dtype_of(int32_t flags, const LaunchPlan& lp, int* dtype) {
+    const int both = DMEL_FLAG_X_I16 | DMEL_FLAG_X_F16;
+    if ((flags & both) == both) return DMEL_ERR_BAD_GEOMETRY;
+    *dtype = (flags & DMEL_FLAG_X_I16) ? DMEL_X_I16 : ((flags & DMEL_FLAG_X_F16) ? DMEL_X_F16 : DMEL_X_F32);
+    if (*dtype != DMEL_X_F32 && !(lp.path == 0 && lp.gen == 2)) return DMEL_ERR_UNSUPPORTED_NFFT;
+    return DMEL_OK;
+}
+
+// spans move as 16-byte quads (fp32) / 8-byte quads (16-bit samples) when x and its row stride allow
+static int row_alignment_ok(const void* x, int64_t stride, int dtype) {
+    const uintptr_t mask = dtype == DMEL_X_F32 ? 15 : 7;
+    return ((reinterpret_cast<uintptr_t>(x) & mask) == 0 && (stride & 3) == 0) ? 1 : 0;
+}
+
+static int forward_impl(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
                         int32_t win_length, int32_t n_fft, int32_t hop, int32_t n_mels, const dmel_melbank* bank,
                         float log_eps, int32_t flags, float* y, float* dy, void* workspace, size_t workspace_bytes,
                         void* cuda_stream) {
@@ -585,36 +749,51 @@ static int forward_impl(const float* x, int64_t batch, int64_t n_points, int64_t
     const int rows = spec ? n_fft / 2 + 1 : n_mels;
     LaunchPlan lp{};
     if ((rc = plan_launch(batch, n_points, n_fft, hop, rows, spec ? 0 : round_up4(n_mels) + round_up4(n_mels + 1), spec ? 0 : bank->mel_nnz, false,
-                          false, &lp, dy != nullptr)))
+                          false, &lp, dy != nullptr, !spec && bank->seg_tables != nullptr)))
         return rc;
     if (dy && lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;   // the JVP forward exists for the tiled FFT path only
     if ((flags & DMEL_FLAG_TIME_MAJOR) && lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;   // likewise the (B,1,T,M) layout
     if (int64_t(batch) * lp.tiles_per_clip > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
+    int x_dtype = DMEL_X_F32;
+    if ((rc = x_dtype_of(flags, lp, &x_dtype))) return rc;
+    const bool gen2 = lp.path == 0 && lp.gen == 2;
     WsView ws = ws_view(workspace, batch, n_fft);
-    if ((rc = run_prep(x, batch, n_points, x_row_stride, fabsf(lambda), win_length, n_fft, flags, ws, st)))
+    const MelDev mel = mel_dev(bank);
+    if ((rc = run_prep(x, batch, n_points, x_row_stride, fabsf(lambda), win_length, n_fft, flags, ws, st, gen2)))
         return rc;
     Geom g = make_geom(batch, n_points, x_row_stride, n_fft, hop, rows, log_eps, lp);
-    g.row_aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_row_stride & 3) == 0) ? 1 : 0;
+    g.x_dtype = x_dtype;
+    g.row_aligned = row_alignment_ok(x, x_row_stride, x_dtype);
     g.time_major = (flags & DMEL_FLAG_TIME_MAJOR) ? 1 : 0;
-    const MelDev mel = mel_dev(bank);
+    const float* xf = static_cast<const float*>(x);
+#ifdef DMEL_FAST_BUILD
+    if (lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;
+#else
     if (lp.path == 1) {
         if ((rc = set_smem(dmel_dft_kernel<false, false>, lp.smem))) return rc;
         ProfScope prof(PROF_FWD, st);
         dmel_dft_kernel<false, false><<<unsigned(int64_t(g.B) * g.T), DFT_THREADS, lp.smem, st>>>(
-            x, nullptr, nullptr, y, nullptr, g, mel, spec ? 1 : 0, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
+            xf, nullptr, nullptr, y, nullptr, g, mel, spec ? 1 : 0, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
         return check_launch("dmel_dft_kernel<fwd>");
     }
     if (lp.path == 2) {
-        return n_fft == 8192 ? launch_big_fwd<8192>(x, y, g, mel, spec, ws, lp, st)
-                             : launch_big_fwd<16384>(x, y, g, mel, spec, ws, lp, st);
+        return n_fft == 8192 ? launch_big_fwd<8192>(xf, y, g, mel, spec, ws, lp, st)
+                             : launch_big_fwd<16384>(xf, y, g, mel, spec, ws, lp, st);
     }
-#define CALL_FWD(LL, NGG) launch_fwd<LL, NGG>(x, y, dy, g, mel, spec, ws, lp, st)
+#endif
+    if (gen2) {
+#define CALL_FWD2(LL, NGG) launch_fwd2<LL, NGG>(x, y, dy, g, mel, spec, ws, lp, st)
+        DMEL_DISPATCH2(n_fft, lp.NG, CALL_FWD2)
+#undef CALL_FWD2
+        return rc;
+    }
+#define CALL_FWD(LL, NGG) launch_fwd<LL, NGG>(xf, y, dy, g, mel, spec, ws, lp, st)
     DMEL_DISPATCH(n_fft, lp.NG, CALL_FWD)
 #undef CALL_FWD
     return rc;
 }
 
-extern "C" DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
+extern "C" DMEL_API int dmel_forward_f32(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
                                 int32_t win_length, int32_t n_fft, int32_t hop, int32_t n_mels,
                                 const dmel_melbank* bank, float log_eps, int32_t flags, float* y,
                                 void* workspace, size_t workspace_bytes, void* cuda_stream) {
@@ -622,7 +801,7 @@ extern "C" DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t 
                         nullptr, workspace, workspace_bytes, cuda_stream);
 }
 
-extern "C" DMEL_API int dmel_forward_jvp_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
+extern "C" DMEL_API int dmel_forward_jvp_f32(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
                                     float lambda, int32_t win_length, int32_t n_fft, int32_t hop, int32_t n_mels,
                                     const dmel_melbank* bank, float log_eps, int32_t flags, float* y,
                                     float* dy_dlambda, void* workspace, size_t workspace_bytes, void* cuda_stream) {
@@ -632,6 +811,36 @@ extern "C" DMEL_API int dmel_forward_jvp_f32(const float* x, int64_t batch, int6
 }
 
 extern "C" DMEL_API int dmel_jvp_supported(int32_t n_fft) { const FftInfo fi = fft_info(n_fft); return (fi.ok && !fi.big) ? 1 : 0; }
+
+extern "C" DMEL_API int dmel_x16_supported(int32_t n_fft) { return fft2_info(n_fft).ok ? 1 : 0; }
+
+extern "C" DMEL_API size_t dmel_segment_table_bytes(int32_t n_fft) {
+    return fft2_info(n_fft).ok ? seg_blob_bytes(n_fft) : 0;
+}
+
+extern "C" DMEL_API int dmel_build_segment_tables(const dmel_melbank* bank, int32_t n_fft, void* tables, size_t bytes,
+                                                  void* cuda_stream, int32_t* usable) {
+    if (usable) *usable = 0;
+    if (!bank || !tables) return DMEL_ERR_NULL_POINTER;
+    if (!fft2_info(n_fft).ok) return DMEL_ERR_UNSUPPORTED_NFFT;
+    if (bank->n_freqs != n_fft / 2 + 1 || bank->n_mels <= 0) return DMEL_ERR_BAD_MELBANK;
+    if (!bank->bin_m0 || !bank->bin_off || !bank->bin_w) return DMEL_ERR_NULL_POINTER;
+    if (bytes < seg_blob_bytes(n_fft)) return DMEL_ERR_WORKSPACE_TOO_SMALL;
+    if (reinterpret_cast<uintptr_t>(tables) & 15) return DMEL_ERR_BAD_MELBANK;
+    MelDev m{};
+    m.bin_m0 = bank->bin_m0; m.bin_off = bank->bin_off; m.bin_w = bank->bin_w;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    dmel_segment_kernel<<<1, PREP_THREADS, 0, st>>>(m, bank->n_mels, n_fft, n_fft / 16, seg_view(tables, n_fft));
+    int rc = check_launch("dmel_segment_kernel");
+    if (rc) return rc;
+    // one-time set-up call: read the verdict back (this is the only entry point that synchronises its stream)
+    SegHeader h{};
+    if (cudaMemcpyAsync(&h, tables, sizeof(h), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+        return check_launch("dmel_build_segment_tables readback") ? DMEL_ERR_LAUNCH_FAILED : DMEL_ERR_LAUNCH_FAILED;
+    if (usable) *usable = h.use_seg ? 1 : 0;
+    return DMEL_OK;
+}
 
 extern "C" DMEL_API int dmel_lambda_grad_f32(const float* grad_y, const float* dy_dlambda, int64_t count, float lambda,
                                     float* grad_lambda, void* workspace, size_t workspace_bytes, void* cuda_stream) {
@@ -648,7 +857,7 @@ extern "C" DMEL_API int dmel_lambda_grad_f32(const float* grad_y, const float* d
     return check_launch("dmel_lambda_grad_kernel");
 }
 
-static int backward_impl(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
+static int backward_impl(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
                          int32_t win_length, int32_t n_fft, int32_t hop, int32_t n_mels, const dmel_melbank* bank,
                          float log_eps, int32_t flags, const float* y, const float* grad_y, float* grad_x,
                          float* grad_lambda, void* workspace, size_t workspace_bytes, int32_t prepared,
@@ -666,9 +875,13 @@ static int backward_impl(const float* x, int64_t batch, int64_t n_points, int64_
                           spec ? 0 : bank->bin_nnz, true, need_dx, &lp)))
         return rc;
     if (int64_t(batch) * lp.tiles_per_clip > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
+    int x_dtype = DMEL_X_F32;
+    if ((rc = x_dtype_of(flags, lp, &x_dtype))) return rc;
+    const bool gen2 = lp.path == 0 && lp.gen == 2;
+    const float* xf = static_cast<const float*>(x);
     WsView ws = ws_view(workspace, batch, n_fft);
     if (!prepared) {
-        if ((rc = run_prep(x, batch, n_points, x_row_stride, fabsf(lambda), win_length, n_fft, flags, ws, st)))
+        if ((rc = run_prep(x, batch, n_points, x_row_stride, fabsf(lambda), win_length, n_fft, flags, ws, st, gen2)))
             return rc;
     }
     // zero the accumulators (and dx: halo positions are reduced with atomics) in one launch
@@ -681,29 +894,40 @@ static int backward_impl(const float* x, int64_t batch, int64_t n_points, int64_
         if ((rc = check_launch("dmel_zero_kernel"))) return rc;
     }
     Geom g = make_geom(batch, n_points, x_row_stride, n_fft, hop, rows, log_eps, lp);
-    g.row_aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_row_stride & 3) == 0) ? 1 : 0;
+    g.x_dtype = x_dtype;
+    g.row_aligned = row_alignment_ok(x, x_row_stride, x_dtype);
     g.time_major = (flags & DMEL_FLAG_TIME_MAJOR) ? 1 : 0;
     if (g.time_major && lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;
     const MelDev mel = mel_dev(bank);
+#ifdef DMEL_FAST_BUILD
+    if (lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;
+    if (false) {
+#else
     if (lp.path == 1) {
         const unsigned grid = unsigned(int64_t(g.B) * g.T);
         ProfScope prof(PROF_BWD, st);
         if (need_dx) {
             if ((rc = set_smem(dmel_dft_kernel<true, true>, lp.smem))) return rc;
             dmel_dft_kernel<true, true><<<grid, DFT_THREADS, lp.smem, st>>>(
-                x, y, grad_y, nullptr, grad_x, g, mel, spec ? 1 : 0, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
+                xf, y, grad_y, nullptr, grad_x, g, mel, spec ? 1 : 0, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
         } else {
             if ((rc = set_smem(dmel_dft_kernel<true, false>, lp.smem))) return rc;
             dmel_dft_kernel<true, false><<<grid, DFT_THREADS, lp.smem, st>>>(
-                x, y, grad_y, nullptr, nullptr, g, mel, spec ? 1 : 0, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
+                xf, y, grad_y, nullptr, nullptr, g, mel, spec ? 1 : 0, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
         }
         if ((rc = check_launch("dmel_dft_kernel<bwd>"))) return rc;
     } else if (lp.path == 2) {
-        rc = n_fft == 8192 ? launch_big_bwd<8192>(x, y, grad_y, grad_x, g, mel, spec, ws, lp, st)
-                           : launch_big_bwd<16384>(x, y, grad_y, grad_x, g, mel, spec, ws, lp, st);
+        rc = n_fft == 8192 ? launch_big_bwd<8192>(xf, y, grad_y, grad_x, g, mel, spec, ws, lp, st)
+                           : launch_big_bwd<16384>(xf, y, grad_y, grad_x, g, mel, spec, ws, lp, st);
+        if (rc) return rc;
+#endif
+    } else if (gen2) {
+#define CALL_BWD2(LL, NGG) launch_bwd2<LL, NGG>(x, y, grad_y, grad_x, g, mel, spec, ws, lp, st)
+        DMEL_DISPATCH2(n_fft, lp.NG, CALL_BWD2)
+#undef CALL_BWD2
         if (rc) return rc;
     } else {
-#define CALL_BWD(LL, NGG) launch_bwd<LL, NGG>(x, y, grad_y, grad_x, g, mel, spec, ws, lp, st)
+#define CALL_BWD(LL, NGG) launch_bwd<LL, NGG>(xf, y, grad_y, grad_x, g, mel, spec, ws, lp, st)
         DMEL_DISPATCH(n_fft, lp.NG, CALL_BWD)
 #undef CALL_BWD
         if (rc) return rc;
@@ -723,7 +947,7 @@ static int backward_impl(const float* x, int64_t batch, int64_t n_points, int64_
     return check_launch("dmel_finalize_kernel");
 }
 
-extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
+extern "C" DMEL_API int dmel_backward_f32(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
                                  int32_t win_length, int32_t n_fft, int32_t hop, int32_t n_mels,
                                  const dmel_melbank* bank, float log_eps, int32_t flags, const float* y,
                                  const float* grad_y, float* grad_x, float* grad_lambda, void* workspace,
@@ -732,7 +956,7 @@ extern "C" DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t
                          grad_y, grad_x, grad_lambda, workspace, workspace_bytes, prepared, cuda_stream, nullptr, 0, 1);
 }
 
-extern "C" DMEL_API int dmel_backward_allreduce_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
+extern "C" DMEL_API int dmel_backward_allreduce_f32(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
                                            float lambda, int32_t win_length, int32_t n_fft, int32_t hop,
                                            int32_t n_mels, const dmel_melbank* bank, float log_eps, int32_t flags,
                                            const float* y, const float* grad_y, float* grad_x, float* grad_lambda,

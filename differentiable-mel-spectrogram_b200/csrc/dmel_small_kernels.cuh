@@ -2,6 +2,7 @@
 // Part of libdmel_b200.so (single translation unit, see dmel_kernels.cu for the overview).
 #pragma once
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 
 #include "dmel_common.cuh"
 
@@ -29,10 +30,94 @@ __host__ __device__ inline int prep_segments(int N) {
     return s < 1 ? 1 : (s > PREP_MAX_SEGMENTS ? PREP_MAX_SEGMENTS : s);
 }
 
+// Segment tables of the second-generation forward (SegHeader in dmel_common.cuh), built by one CTA from the bin-major
+// bank.  gt = threads per FFT group (n_fft/16); gt == 0: not wanted (spectrogram mode, other kernel families).
+constexpr int SEG_MAX_MELS = 1024;
+__global__ void __launch_bounds__(PREP_THREADS)
+dmel_segment_kernel(MelDev mel, int n_mels, int n_fft, int gt, SegView sv) {
+    __shared__ int seg_start[SEG_MAX_MELS], seg_len[SEG_MAX_MELS];
+    __shared__ int pass_max[SEG_MAX_PASSES], pass_base[SEG_MAX_PASSES + 1];
+    __shared__ int bad;
+    const int tid = threadIdx.x, F = n_fft / 2 + 1;
+    const int npass = gt > 0 ? (n_mels + gt - 1) / gt : 0;
+    const int cap = seg_capacity(n_fft), pitch = gt + 1;
+    if (gt <= 0 || n_mels <= 0 || n_mels > SEG_MAX_MELS || npass > SEG_MAX_PASSES || mel.bin_m0 == nullptr) {
+        if (tid == 0) sv.hdr->use_seg = 0;
+        return;
+    }
+    if (tid == 0) bad = 0;
+    for (int m = tid; m < n_mels; m += PREP_THREADS) { seg_start[m] = -1; seg_len[m] = 0; }
+    if (tid < SEG_MAX_PASSES) pass_max[tid] = 0;
+    __syncthreads();
+    auto seg_of = [&](int k) {   // segment of bin k, -1 if the bin carries no weight
+        const int o0 = __ldg(mel.bin_off + k), cnt = __ldg(mel.bin_off + k + 1) - o0;
+        if (cnt > 2) bad = 1;
+        return cnt > 0 ? __ldg(mel.bin_m0 + k) : -1;
+    };
+    // segment starts; a segment that starts twice (weights interrupted by an empty bin) or a bank whose first mels do
+    // not increase with frequency is not of the expected shape
+    for (int k = tid; k < F; k += PREP_THREADS) {
+        const int sk = seg_of(k);
+        if (sk >= n_mels) bad = 1;
+        if (sk >= 0 && sk < n_mels) {
+            const int sp = k > 0 ? seg_of(k - 1) : -1;
+            if (sp != sk) {
+                if (atomicCAS(&seg_start[sk], -1, k) != -1) bad = 1;
+            }
+            if (sp > sk) bad = 1;
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < F; k += PREP_THREADS) {
+        const int sk = seg_of(k);
+        if (sk >= 0 && sk < n_mels && seg_start[sk] >= 0) {
+            const int j = k - seg_start[sk];
+            if (j < 0) bad = 1;
+            else atomicMax(&seg_len[sk], j + 1);
+        }
+    }
+    __syncthreads();
+    for (int m = tid; m < n_mels; m += PREP_THREADS) atomicMax(&pass_max[m / gt], seg_len[m]);
+    __syncthreads();
+    if (tid == 0) {
+        int o = 0;
+        for (int i = 0; i < npass; ++i) { pass_base[i] = o; o += pass_max[i]; }
+        pass_base[npass] = o;
+        // slots [0, nslot*pitch) hold the segments, slot nslot*pitch is the dummy bins without weights are written to
+        const int use = (!bad && o * pitch + 1 <= cap) ? 1 : 0;
+        sv.hdr->use_seg = use;
+        sv.hdr->npass = npass;
+        sv.hdr->nslot = o;
+        sv.hdr->pad_ = 0;
+        for (int i = 0; i < SEG_MAX_PASSES; ++i) {
+            sv.hdr->base[i] = i < npass ? pass_base[i] : 0;
+            sv.hdr->maxlen[i] = i < npass ? pass_max[i] : 0;
+        }
+        if (!use) bad = 1;
+    }
+    __syncthreads();
+    if (bad) return;
+    const int nslot = pass_base[npass];
+    for (int i = tid; i < cap; i += PREP_THREADS) sv.w[i] = make_float2(0.f, 0.f);
+    __syncthreads();
+    for (int k = tid; k < F; k += PREP_THREADS) {
+        const int o0 = __ldg(mel.bin_off + k), cnt = __ldg(mel.bin_off + k + 1) - o0;
+        int dest = nslot * pitch;
+        if (cnt > 0) {
+            const int sk = __ldg(mel.bin_m0 + k);
+            const int slot = (pass_base[sk / gt] + (k - seg_start[sk])) * pitch + (sk % gt);
+            sv.w[slot] = make_float2(__ldg(mel.bin_w + o0), cnt > 1 ? __ldg(mel.bin_w + o0 + 1) : 0.f);
+            dest = slot;
+        }
+        sv.dest[k] = dest;
+    }
+}
+
 // grid = (B + 1) clusters of prep_segments(N) CTAs: cluster b < B -> mean of clip b; cluster B -> window + twiddles
 __global__ void __launch_bounds__(PREP_THREADS)
-dmel_prep_kernel(const float* __restrict__ x, long long x_stride, int B, int N, float lam_abs, int win_length,
+dmel_prep_kernel(const void* __restrict__ x_any, long long x_stride, int B, int N, float lam_abs, int win_length,
                  int n_fft, int flags, WsView ws, PlanDesc plan) {
+    const float* x = static_cast<const float*>(x_any);
     __shared__ double red[32];
     __shared__ double seg_total;
     const int tid = threadIdx.x;
@@ -45,13 +130,33 @@ dmel_prep_kernel(const float* __restrict__ x, long long x_stride, int B, int N, 
             return;
         }
         // models.py:38  x[idx] - torch.mean(x[idx])
-        const int seg_len = (((N + nseg - 1) / nseg) + 3) & ~3;       // multiple of 4: segments keep x's alignment
+        const bool x16 = (flags & (DMEL_FLAG_X_I16 | DMEL_FLAG_X_F16)) != 0;
+        const int seg_len = x16 ? ((((N + nseg - 1) / nseg) + 7) & ~7)
+                                : ((((N + nseg - 1) / nseg) + 3) & ~3);   // segments keep x's 16-byte alignment
         const int lo = min(seg * seg_len, N), hi = min(lo + seg_len, N);
         const float* xb = x + (long long)clip * x_stride + lo;
         const int n = hi - lo;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int i0 = 0;
-        if ((reinterpret_cast<uintptr_t>(xb) & 15) == 0) {
+        if (x16) {
+            // 16-bit samples (int16 PCM or half), widened exactly like the staging of the main kernels
+            const bool is_i16 = (flags & DMEL_FLAG_X_I16) != 0;
+            const unsigned short* xh = static_cast<const unsigned short*>(x_any) + (long long)clip * x_stride + lo;
+            auto wide = [&](unsigned v) {
+                return is_i16 ? float(short(v & 0xffffu)) : __half2float(__ushort_as_half((unsigned short)(v & 0xffffu)));
+            };
+            if ((reinterpret_cast<uintptr_t>(xh) & 15) == 0) {
+                const uint4* x8 = reinterpret_cast<const uint4*>(xh);
+                const int n8 = n >> 3;
+                for (int q = tid; q < n8; q += PREP_THREADS) {
+                    const uint4 v = __ldg(x8 + q);
+                    acc[0] += ((wide(v.x) + wide(v.x >> 16)) + (wide(v.y) + wide(v.y >> 16))) +
+                                  ((wide(v.z) + wide(v.z >> 16)) + (wide(v.w) + wide(v.w >> 16)));
+                }
+                i0 = n8 << 3;
+            }
+            for (int i = i0 + tid; i < n; i += PREP_THREADS) acc[1] += wide(__ldg(xh + i));
+        } else if ((reinterpret_cast<uintptr_t>(xb) & 15) == 0) {
             // 16-byte loads, 8 independent ones in flight per thread
             const float4* x4 = reinterpret_cast<const float4*>(xb);
             const int n4 = n >> 2;
@@ -69,7 +174,8 @@ dmel_prep_kernel(const float* __restrict__ x, long long x_stride, int B, int N, 
             }
             i0 = n4 << 2;
         }
-        for (int i = i0 + tid; i < n; i += PREP_THREADS) acc[1] += __ldg(xb + i);
+        if (!x16)
+            for (int i = i0 + tid; i < n; i += PREP_THREADS) acc[1] += __ldg(xb + i);
         double part = 0.0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) part += double(acc[u]);

@@ -131,6 +131,24 @@ class DeviceBank:
         s.mel_nnz, s.bin_nnz = int(packed.mel_off[-1]), int(packed.bin_off[-1])
         s.mel_k0, s.mel_off, s.bin_m0, s.bin_off, s.mel_w, s.bin_w = (base + 4 * o for o in offs)
         self.struct = s
+        # segment tables of the tiled forward (dmel.h: dmel_build_segment_tables): built once per bank by the library
+        from . import _lib
+        lib = _lib.load()
+        n_fft = 2 * (packed.n_freqs - 1)
+        nbytes = int(lib.dmel_segment_table_bytes(n_fft))
+        self._seg = None
+        if nbytes:
+            self._seg = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+            idx = device.index if device.index is not None else torch.cuda.current_device()
+            with torch.cuda.device(idx):
+                stream = int(torch._C._cuda_getCurrentRawStream(idx))
+                usable = ctypes.c_int32(0)
+                _lib.check(lib.dmel_build_segment_tables(ctypes.byref(s), n_fft, self._seg.data_ptr(), nbytes, stream,
+                                                         ctypes.byref(usable)), "dmel_build_segment_tables")
+            if usable.value:
+                s.seg_tables = self._seg.data_ptr()
+            else:
+                self._seg = None
 
     def ref(self):
         return ctypes.byref(self.struct)

@@ -242,7 +242,13 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
     _require_cuda(x, "x")
     if lambd.numel() != 1:
         raise ValueError("lambd must hold exactly one element")
-    if x.dtype != torch.float32:
+    # 16-bit samples (int16 PCM — the datasets' native format, datasets.py:169,208,255 — or fp16) are widened inside
+    # the kernels while the signal is staged (no intermediate fp32 tensor) when the tiled FFT path serves this n_fft and
+    # no gradient with respect to x is wanted; every other dtype is cast to fp32 first, as before
+    x16_flag = 0
+    if x.dtype in (torch.int16, torch.float16) and not x.requires_grad:
+        x16_flag = _lib.FLAG_X_I16 if x.dtype == torch.int16 else _lib.FLAG_X_F16
+    elif x.dtype != torch.float32:
         x = x.to(torch.float32)
     if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
         x = x.contiguous()
@@ -256,7 +262,7 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
         raise ValueError("log_eps must be >= 0")
     # everything below depends only on these scalars: resolve once, reuse while they repeat (training loops)
     key = (B, N, hop_length, lam_value, optimized, normalize_window, n_mels, sample_rate, f_min, f_max, log_eps, remove_mean,
-           time_major, x.device.index)
+           time_major, x.device.index, x16_flag)
     plan = _plan_cache.get(key)
     if plan is None:
         geo = resolve_geometry(B, N, hop_length, lam_value, optimized, n_mels)
@@ -269,6 +275,8 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
             bank = device_bank(geo.n_freqs, f_min, fmax, n_mels, sample_rate, x.device)
         flags = ((_lib.FLAG_NORMALIZE_WINDOW if normalize_window else 0) | (0 if remove_mean else _lib.FLAG_KEEP_MEAN)
                  | (_lib.FLAG_TIME_MAJOR if time_major else 0))
+        if x16_flag and lib.dmel_x16_supported(geo.n_fft):
+            flags |= x16_flag
         if time_major and not lib.dmel_jvp_supported(geo.n_fft):
             raise _lib.DmelError(f"time_major output is implemented for n_fft 128..4096, got {geo.n_fft}")
         eps = -1.0 if log_eps is None else float(log_eps)
@@ -277,6 +285,8 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
             _plan_cache.clear()
         _plan_cache[key] = plan
     geo, bank, eps, flags, ws_bytes = plan
+    if x16_flag and not (flags & x16_flag):
+        x = x.to(torch.float32)        # this n_fft is served by a kernel family without 16-bit staging
     if out_affine is not None:
         if bank is None:
             raise ValueError("out_affine needs n_mels > 0 (it is a per-mel map)")

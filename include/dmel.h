@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DMEL_ABI_VERSION 2
+#define DMEL_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define DMEL_API __attribute__((visibility("default")))
@@ -40,6 +40,16 @@ extern "C" {
 #define DMEL_FLAG_NORMALIZE_WINDOW 1
 #define DMEL_FLAG_KEEP_MEAN 2
 #define DMEL_FLAG_TIME_MAJOR 4   /* y, grad_y, dy_dlambda are [batch,1,T,rows] (rows fastest) instead of [batch,1,rows,T] */
+/* Input sample type (ABI 3).  `x` is declared const void*: fp32 by default; with one of these flags it points to
+ * 16-bit samples that the kernels widen while they stage the signal — float(int16) exactly as torch's
+ * x.to(torch.float32) (no 1/32768 scaling), or IEEE half -> float.  This is the PCM input path of the reference's
+ * data loaders (datasets.py:169,208,255 -> train.py:34) without the intermediate fp32 tensor and with half the
+ * host->device bytes.  Tiled FFT path (n_fft 256..4096) only: dmel_x16_supported().                               */
+#define DMEL_FLAG_X_I16 8
+#define DMEL_FLAG_X_F16 16
+#define DMEL_X_F32 0
+#define DMEL_X_I16 1
+#define DMEL_X_F16 2
 
 typedef enum dmel_status {
     DMEL_OK = 0,
@@ -84,7 +94,21 @@ typedef struct dmel_melbank {
     const float* bin_w;       /* [bin_off[F]]                                           */
     const float* out_scale;   /* [M] or NULL                                            */
     const float* out_shift;   /* [M] or NULL                                            */
+    const void* seg_tables;   /* device memory filled by dmel_build_segment_tables for this bank and
+                                 n_fft = 2*(F-1), or NULL (ABI 3): the forward then projects segment by
+                                 segment (conflict-free shared-memory layout) instead of mel by mel    */
 } dmel_melbank;
+
+/* Optional, once per (bank, n_fft): derive from the bin-major form the lane-owned "segment" tables the tiled forward
+ * (n_fft 256..4096) uses for the mel projection.  `tables` is caller-owned device memory of at least
+ * dmel_segment_table_bytes(n_fft) bytes, 16-byte aligned; store its address in bank->seg_tables afterwards.
+ * Banks that are not triangular (more than two mels per bin, runs that do not move up with frequency) or whose tables
+ * would not fit next to the transform buffer give *usable = 0: leave seg_tables NULL then (the forward keeps the
+ * mel-major gather — results are the same either way).  A set-up call: unlike every other entry point it waits for
+ * its stream.                                                                                                     */
+DMEL_API size_t dmel_segment_table_bytes(int32_t n_fft);
+DMEL_API int dmel_build_segment_tables(const dmel_melbank* bank, int32_t n_fft, void* tables, size_t bytes,
+                              void* cuda_stream, int32_t* usable);
 
 DMEL_API int dmel_abi_version(void);
 DMEL_API const char* dmel_status_string(int status);
@@ -108,7 +132,7 @@ DMEL_API size_t dmel_workspace_y_sum_offset(void);
 
 /* Forward:  y[b,0,m,t] of models.py:33-56 (n_mels > 0) or models.py:182-200
  * (n_mels == 0: "spectrogram mode", rows are the n_fft/2+1 frequency bins).
- *   x           [batch, n_points] fp32, row stride x_row_stride elements
+ *   x           [batch, n_points] fp32 (or 16-bit, see DMEL_FLAG_X_*), row stride x_row_stride elements
  *   lambda      the layer's parameter `lambd` (signed; |.| is taken as models.py:38)
  *   win_length  Gaussian window length: next_power_of_2(6|lambda|) when optimized,
  *               n_points otherwise (time_frequency.py:34-43)
@@ -125,7 +149,7 @@ DMEL_API size_t dmel_workspace_y_sum_offset(void);
  *   y           [batch, 1, rows, T] fp32 contiguous, rows = n_mels or n_fft/2+1
  *   workspace   >= dmel_workspace_bytes(batch, n_fft); filled here (means, window,
  *               twiddles) and reusable by dmel_backward_f32 with prepared = 1      */
-DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
+DMEL_API int dmel_forward_f32(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
                      float lambda, int32_t win_length, int32_t n_fft, int32_t hop,
                      int32_t n_mels, const dmel_melbank* bank, float log_eps,
                      int32_t flags, float* y,
@@ -138,7 +162,9 @@ DMEL_API int dmel_forward_f32(const float* x, int64_t batch, int64_t n_points, i
  * backward a dot product (dmel_lambda_grad_f32): 1.0 instead of 1.5 FFTs per frame per training step, no
  * recomputation.  Tiled FFT path only (dmel_jvp_supported: n_fft 128..4096).                              */
 DMEL_API int dmel_jvp_supported(int32_t n_fft);
-DMEL_API int dmel_forward_jvp_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
+/* 1 if 16-bit inputs (DMEL_FLAG_X_I16 / DMEL_FLAG_X_F16) are accepted for this transform length */
+DMEL_API int dmel_x16_supported(int32_t n_fft);
+DMEL_API int dmel_forward_jvp_f32(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
                          float lambda, int32_t win_length, int32_t n_fft, int32_t hop,
                          int32_t n_mels, const dmel_melbank* bank, float log_eps,
                          int32_t flags, float* y, float* dy_dlambda,
@@ -157,7 +183,7 @@ DMEL_API int dmel_lambda_grad_f32(const float* grad_y, const float* dy_dlambda, 
  *   grad_lambda  one fp32: dL/dlambda (includes sign(lambda) from torch.abs)
  *   prepared     1: workspace still holds what dmel_forward_f32 wrote for the same
  *                (x, lambda, geometry); 0: recompute means/window/twiddles first    */
-DMEL_API int dmel_backward_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
+DMEL_API int dmel_backward_f32(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
                       float lambda, int32_t win_length, int32_t n_fft, int32_t hop,
                       int32_t n_mels, const dmel_melbank* bank, float log_eps,
                       int32_t flags, const float* y, const float* grad_y,
@@ -188,7 +214,7 @@ DMEL_API int dmel_peer_allreduce_f32(float* value, const void* peer_bases_dev, i
 /* dmel_backward_f32 with the collective fused in: the finalize kernel that converts the fp64 dL/dlambda sum also
  * exchanges it with the peers (same protocol as dmel_peer_allreduce_f32, same buffers) while its other blocks apply
  * the mean-removal adjoint to grad_x; grad_lambda receives the sum over all `world` GPUs.  No separate launch.       */
-DMEL_API int dmel_backward_allreduce_f32(const float* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
+DMEL_API int dmel_backward_allreduce_f32(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
                                 float lambda, int32_t win_length, int32_t n_fft, int32_t hop,
                                 int32_t n_mels, const dmel_melbank* bank, float log_eps,
                                 int32_t flags, const float* y, const float* grad_y,

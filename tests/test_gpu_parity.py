@@ -565,6 +565,102 @@ def test_random_geometries_against_oracle(cuda_device, B, N, hop, lam, M, norm, 
     # the oracle's own fp32 gradient noise grows with cancellation; fall back to its fp64 run when it is the outlier
     try:
         check_grads(got[1], got[2], want[1], want[2])
-    except AssertionError:
+    except AssertionError as first:
+        # logged (pytest -rA / captured output), so that a kernel drifting towards the bar cannot hide in this branch
+        print(f"[fp64 fallback] B={B} N={N} hop={hop} lam={lam} M={M} norm={norm} log={use_log} n_fft={n_fft}: "
+              f"fp32 oracle comparison failed ({str(first).splitlines()[0][:120]}); comparing with the fp64 oracle")
+        FP64_FALLBACKS.append((B, N, hop, lam, M, norm, use_log, n_fft))
         want64 = orc.port_forward_backward(x, lam, G, use_log=use_log, batched=True, dtype=torch.float64, **kw_o)
         check_grads(got[1], got[2], np.asarray(want64[1], dtype=np.float64), float(want64[2]))
+
+
+FP64_FALLBACKS = []
+
+
+def test_fp64_fallback_stays_rare():
+    """Runs after the sweep above (file order): at most a handful of the 28 seeded geometries may need the fp64 oracle
+    (round 1: 2).  A kernel whose fp32 error grows shows up here first."""
+    assert len(FP64_FALLBACKS) <= 4, FP64_FALLBACKS
+
+
+# ------------------------------------------------------------------------------------------ round 2 additions
+@pytest.mark.parametrize("dtype", [torch.int16, torch.float16])
+@pytest.mark.parametrize("B,N,sr,hop,M,lam", [
+    (5, 8000, 8000, 80, 64, 8000 * 0.035 / 6),          # n_fft 512
+    (2, 16001, 16000, 160, 128, 16000 * 0.035 / 6),     # n_fft 1024, odd length: rows are not 8-byte aligned
+    (2, 22050, 44100, 441, 128, 44100 * 0.035 / 6),     # n_fft 2048
+])
+def test_sixteen_bit_samples_are_widened_in_kernel(cuda_device, dtype, B, N, sr, hop, M, lam):
+    """int16 PCM / fp16 clips go to the kernels as they are (DMEL_FLAG_X_I16 / _F16, dmel.h) and must
+    give what the oracle gives on x.to(float32) — forward, the forward-mode lambda gradient and the recomputing one."""
+    dev = cuda_device
+    lib = dm.load()
+    assert lib.dmel_x16_supported(orc.window_length(lam, N, True)[1])
+    g = torch.Generator().manual_seed(11)
+    xf = torch.randn(B, N, generator=g)
+    x16 = (xf * 3000.0).round().clamp(-32768, 32767).to(torch.int16) if dtype == torch.int16 else xf.to(torch.float16)
+    G = torch.randn(B, 1, M, N // hop + 1, generator=g)
+    want = orc.port_forward_backward(x16.to(torch.float32), lam, G, use_log=True, batched=True, hop=hop, optimized=True,
+                                     n_mels=M, sample_rate=sr)
+    for use_jvp in (True, False):
+        dm.op.USE_JVP = use_jvp
+        try:
+            ll = torch.tensor(float(lam), device=dev, requires_grad=True)
+            xd = x16.to(dev)
+            y = dm.dmel(xd, ll, hop_length=hop, optimized=True, n_mels=M, sample_rate=sr, log_eps=EPS)
+            (y * G.to(dev)).sum().backward()
+        finally:
+            dm.op.USE_JVP = True
+        check_y(y.detach().cpu().numpy(), want[0], False)
+        assert abs(float(ll.grad) - want[2]) <= G_RTOL * abs(want[2]), (use_jvp, float(ll.grad), want[2])
+    # and the same numbers as the fp32 path on the widened tensor, to rounding of the mean
+    y32 = dm.dmel(x16.to(dev).to(torch.float32), ll, hop_length=hop, optimized=True, n_mels=M, sample_rate=sr, log_eps=EPS)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), y32.detach().cpu().numpy(), rtol=Y_RTOL, atol=Y_ATOL)
+
+
+@pytest.mark.parametrize("N,sr,hop,M,lam", [(8000, 8000, 80, 64, 46.667), (16000, 16000, 160, 128, 93.33),
+                                            (4000, 8000, 40, 23, 30.0)])
+def test_segment_projection_equals_mel_major_gather(cuda_device, N, sr, hop, M, lam):
+    """dmel.h dmel_build_segment_tables: with the bank's segment tables the forward projects segment by segment, without
+    them mel by mel — same weights, same sums up to fp32 summation order."""
+    import ctypes
+    from importlib import import_module
+    mb = import_module("differentiable-mel-spectrogram_b200.melbank")
+    dev = cuda_device
+    lib = dm.load()
+    geo = dm.resolve_geometry(3, N, hop, lam, True, M)
+    bank = mb.device_bank(geo.n_freqs, 0.0, sr // 2, M, sr, dev)
+    assert bank.struct.seg_tables, "triangular HTK banks of these sizes have usable segment tables"
+    x = torch.randn(3, N, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    ws = torch.empty(lib.dmel_workspace_bytes(3, geo.n_fft), dtype=torch.uint8, device=dev)
+    outs = []
+    for with_tables in (True, False):
+        s = mb.MelBankStruct()
+        ctypes.memmove(ctypes.byref(s), ctypes.byref(bank.struct), ctypes.sizeof(mb.MelBankStruct))
+        if not with_tables:
+            s.seg_tables = None
+        y = torch.empty(3, 1, M, geo.n_frames, device=dev)
+        rc = lib.dmel_forward_f32(x.data_ptr(), 3, N, N, lam, geo.win_length, geo.n_fft, hop, M, ctypes.byref(s), EPS, 0,
+                                  y.data_ptr(), ws.data_ptr(), ws.numel(), int(torch.cuda.current_stream(dev).cuda_stream))
+        assert rc == 0
+        torch.cuda.synchronize()
+        outs.append(y.cpu().numpy())
+    np.testing.assert_allclose(outs[0], outs[1], rtol=2e-6, atol=2e-6)
+
+
+def test_c_host_runs_the_abi_without_torch(cuda_device):
+    """tests/c/abi_run.cu: cudaMalloc + dmel_forward_f32 + dmel_backward_f32 from a plain C++ process, compared with the
+    oracle's arrays stored in tests/golden/cases/*.bin (scripts/dump_case.py)."""
+    import glob
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "c", "abi_run")
+    if not os.path.exists(exe):
+        import __graft_entry__ as ge
+        ge.build_c_host()
+    cases = sorted(glob.glob(os.path.join(root, "tests", "golden", "cases", "*.bin")))
+    assert len(cases) >= 4
+    for c in cases:
+        out = subprocess.run([exe, "check", c], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0 and "PASS" in out.stdout, (c, out.stdout, out.stderr)

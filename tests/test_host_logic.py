@@ -20,7 +20,7 @@ def test_library_loads_and_exports_header_symbols():
     assert declared == set(dm._lib.EXPORTED_SYMBOLS), declared ^ set(dm._lib.EXPORTED_SYMBOLS)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.dmel_abi_version() == 2
+    assert lib.dmel_abi_version() == 3
     assert lib.dmel_status_string(0) == b"ok"
     assert b"n_fft" in lib.dmel_status_string(-3)
 
@@ -93,9 +93,9 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_device():
 
 
 def test_output_affine_struct_fields_and_batchnorm_folding():
-    # struct dmel_melbank: 4 int32 + 8 pointers (include/dmel.h)
-    assert ctypes.sizeof(dm._lib.MelBankStruct) == 4 * 4 + 8 * 8
-    assert [f[0] for f in dm._lib.MelBankStruct._fields_][-2:] == ["out_scale", "out_shift"]
+    # struct dmel_melbank: 4 int32 + 9 pointers (include/dmel.h, ABI 3: + seg_tables)
+    assert ctypes.sizeof(dm._lib.MelBankStruct) == 4 * 4 + 9 * 8
+    assert [f[0] for f in dm._lib.MelBankStruct._fields_][-3:] == ["out_scale", "out_shift", "seg_tables"]
     # a bank with only one of the two vectors is rejected before anything touches the device
     lib = dm.load()
     s = dm._lib.MelBankStruct()
