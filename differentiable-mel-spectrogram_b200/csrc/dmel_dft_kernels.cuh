@@ -60,7 +60,10 @@ dmel_dft_kernel(const float* __restrict__ x, const float* __restrict__ y_in, con
                 const int k0 = __ldg(mel.mel_k0 + m);
                 const int o0 = __ldg(mel.mel_off + m), o1 = __ldg(mel.mel_off + m + 1);
                 s = 0.f;
-                for (int o = o0; o < o1; ++o) s = fmaf(__ldg(mel.mel_w + o), gp[k0 + (o - o0)], s);
+                // runs are zero-padded to 4 taps (dmel.h): the padded taps may point past the last bin, where gp holds
+                // no spectrum (0 * leftover NaN bits would poison the sum), so the walk stops at bin F-1
+                const int cnt = min(o1 - o0, F - k0);
+                for (int o = 0; o < cnt; ++o) s = fmaf(__ldg(mel.mel_w + o0 + o), gp[k0 + o], s);
             }
             if (do_log) s = logf(s + g.log_eps);
             if (!spec_mode && mel.out_scale) s = affine_out(mel, m, s);

@@ -60,9 +60,22 @@ namespace dmel {
 // host side: planning + dispatch
 // ----------------------------------------------------------------------------
 constexpr size_t SMEM_MAX = 227 * 1024;
-// peer all-reduce spin bound, ~2 s at 2 GHz: far beyond any healthy skew between ranks (graph instantiation,
-// first touch), short enough never to look like a hang
-static constexpr long long PEER_TIMEOUT_CYCLES = 4000000000LL;
+// Peer all-reduce spin bound.  A collective has to wait for its slowest rank however late it is (checkpointing or
+// evaluation on one rank, a data-loader stall, first-iteration set-up): a short bound would hand NaN to the ranks
+// that gave up while the late rank still completes, and the replicated lambda would diverge.  So the default is the
+// order of NCCL's own watchdog (30 minutes at ~2 GHz); DMEL_PEER_TIMEOUT_S overrides it (tests use a small value).
+static long long peer_timeout_cycles() {
+    static const long long cycles = [] {
+        double s = 1800.0;
+        if (const char* e = getenv("DMEL_PEER_TIMEOUT_S")) {
+            const double v = atof(e);
+            if (v > 0.0) s = v;
+        }
+        return (long long)(s * 2.0e9);
+    }();
+    return cycles;
+}
+#define PEER_TIMEOUT_CYCLES peer_timeout_cycles()
 constexpr int NUM_SMS = 148;
 
 template <int L> static PlanDesc plan_desc_of() {

@@ -70,38 +70,78 @@ class PeerRing:
     — one 32-thread launch instead of an NCCL call whose latency (~20 us at 8 ranks) is a fifth of a small
     DMEL step.  All ranks of the group must be GPUs of one box with peer access.  `PeerRing.create()` returns
     None (callers keep using NCCL) when the setup or its self-test against the group's all_reduce fails.
+    Like an NCCL collective, a call waits for its peers for as long as it takes (DMEL_PEER_TIMEOUT_S, default
+    1800 s, bounds it; on expiry the result is NaN on the ranks that gave up and `timed_out()` reports it).
     """
 
     def __init__(self, device: torch.device, group=None):
-        import ctypes
-        lib = _lib.load()
+        """Collective constructor for callers that know every rank will succeed; `create()` is the safe entry point
+        (same collective sequence on every rank whatever fails locally)."""
+        self._init_local(device, group)
+        err = self._alloc()
+        gathered = self._exchange()
+        if err is None:
+            err = self._open(gathered)
+        dist.barrier(group=group)
+        if err is not None:
+            self.close()
+            raise err
+
+    def _init_local(self, device: torch.device, group) -> None:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.device = torch.device(device)
         self._mapped: List[int] = []
         self._own = 0
-        if lib.dmel_peer_buffer_bytes(self.world) == 0:
-            raise _lib.DmelError(f"peer ring supports at most 32 ranks, got {self.world}")
-        with torch.cuda.device(self.device):
-            own = ctypes.c_void_p()
-            handle = ctypes.create_string_buffer(64)
-            _lib.check(lib.dmel_peer_alloc(self.world, ctypes.byref(own), handle), "dmel_peer_alloc")
-            self._own = own.value
-            gathered: List[Optional[bytes]] = [None] * self.world
-            dist.all_gather_object(gathered, handle.raw, group=group)
-            bases = []
-            for r in range(self.world):
-                if r == self.rank:
-                    bases.append(self._own)
-                    continue
-                mapped = ctypes.c_void_p()
-                _lib.check(lib.dmel_peer_open(gathered[r], ctypes.byref(mapped)), "dmel_peer_open")
-                self._mapped.append(mapped.value)
-                bases.append(mapped.value)
-            self.bases = torch.tensor(bases, dtype=torch.int64, device=self.device)
-            torch.cuda.synchronize(self.device)
-        dist.barrier(group=group)
+        self._handle = b""
+        self.bases = None
+
+    def _alloc(self) -> Optional[Exception]:
+        """Local: allocate this rank's buffer.  Returns the error instead of raising."""
+        import ctypes
+        try:
+            lib = _lib.load()
+            if lib.dmel_peer_buffer_bytes(self.world) == 0:
+                raise _lib.DmelError(f"peer ring supports at most 32 ranks, got {self.world}")
+            with torch.cuda.device(self.device):
+                own = ctypes.c_void_p()
+                handle = ctypes.create_string_buffer(64)
+                _lib.check(lib.dmel_peer_alloc(self.world, ctypes.byref(own), handle), "dmel_peer_alloc")
+                self._own = own.value
+                self._handle = handle.raw
+            return None
+        except Exception as e:      # noqa: BLE001 - reported through the group, see create()
+            return e
+
+    def _exchange(self) -> List[Optional[bytes]]:
+        """Collective (always runs): every rank's IPC handle, b"" for a rank whose allocation failed."""
+        gathered: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(gathered, self._handle, group=self.group)
+        return gathered
+
+    def _open(self, gathered: List[Optional[bytes]]) -> Optional[Exception]:
+        """Local: map the peers' buffers.  Returns the error instead of raising."""
+        import ctypes
+        try:
+            if any(not h for h in gathered):
+                raise _lib.DmelError("a peer could not allocate its buffer")
+            lib = _lib.load()
+            with torch.cuda.device(self.device):
+                bases = []
+                for r in range(self.world):
+                    if r == self.rank:
+                        bases.append(self._own)
+                        continue
+                    mapped = ctypes.c_void_p()
+                    _lib.check(lib.dmel_peer_open(gathered[r], ctypes.byref(mapped)), "dmel_peer_open")
+                    self._mapped.append(mapped.value)
+                    bases.append(mapped.value)
+                self.bases = torch.tensor(bases, dtype=torch.int64, device=self.device)
+                torch.cuda.synchronize(self.device)
+            return None
+        except Exception as e:      # noqa: BLE001
+            return e
 
     def close(self) -> None:
         lib = _lib.load()
@@ -134,24 +174,41 @@ class PeerRing:
 
     @staticmethod
     def create(device: torch.device, group=None, trials: int = 4) -> Optional["PeerRing"]:
-        """Build a ring and check it against the group's own all_reduce; None if anything is off."""
+        """Build a ring and check it against the group's own all_reduce; None (ring closed, callers keep using the
+        process group) if anything is off on ANY rank.  Every rank issues the same sequence of collectives whatever
+        fails locally — all_gather_object, barrier, one MIN all-reduce of the set-up flag, `trials` x all_reduce, one
+        MIN all-reduce of the verdict — so a local failure can neither hang nor mis-pair the others."""
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) < 2:
             return None
-        ok = torch.ones(1, device=device)
-        ring = None
-        try:
-            ring = PeerRing(device, group)
-            g = torch.Generator(device=device).manual_seed(17 + ring.rank)
-            for _ in range(trials):
-                v = torch.randn(1, device=device, generator=g)
-                want = v.clone()
-                dist.all_reduce(want, group=group)
+        device = torch.device(device)
+        ring = PeerRing.__new__(PeerRing)
+        ring._init_local(device, group)
+        err = ring._alloc()
+        gathered = ring._exchange()
+        if err is None:
+            err = ring._open(gathered)
+        dist.barrier(group=group)
+        ok = torch.ones(1, device=device) if err is None else torch.zeros(1, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)       # did every rank get its ring up?
+        usable = bool(ok.item())
+        good = torch.ones(1, device=device)
+        g = torch.Generator(device=device).manual_seed(17 + ring.rank)
+        for _ in range(trials):
+            v = torch.randn(1, device=device, generator=g)
+            want = v.clone()
+            dist.all_reduce(want, group=group)
+            if not usable:
+                continue                      # the ring kernels need every rank; the group collective still ran
+            try:
                 got = ring.all_reduce_(v.clone())
                 torch.cuda.synchronize(device)
-                if ring.timed_out() or not torch.isfinite(got).all() or abs(float(got) - float(want)) > 1e-5 * max(1.0, abs(float(want))):
-                    ok.zero_()
-                    break
-        except Exception:
-            ok.zero_()
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)       # all ranks agree on the outcome
-        return ring if bool(ok.item()) and ring is not None else None
+                if ring.timed_out() or not torch.isfinite(got).all() or \
+                        abs(float(got) - float(want)) > 1e-5 * max(1.0, abs(float(want))):
+                    good.zero_()
+            except Exception:       # noqa: BLE001
+                good.zero_()
+        dist.all_reduce(good, op=dist.ReduceOp.MIN, group=group)     # all ranks agree on the outcome
+        if usable and bool(good.item()):
+            return ring
+        ring.close()
+        return None

@@ -125,14 +125,15 @@ class DmelFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x: torch.Tensor, lambd: torch.Tensor, ws: torch.Tensor, geo: Geometry, bank: Optional[DeviceBank],
-                log_eps: float, flags: int, lam_value: float):
+                log_eps: float, flags: int, lam_value: float, jvp: bool):
         lib = _lib.load()
         dev = x.device
         shape = (geo.batch, 1, geo.n_frames, geo.rows) if (flags & _lib.FLAG_TIME_MAJOR) else (geo.batch, 1, geo.rows, geo.n_frames)
         y = torch.empty(shape, dtype=torch.float32, device=dev)
         # The reference's training case: x is data, only lambd trains (models.py:19, main.py:27).  Then dy/dlambda is
         # produced by the forward itself (derivative-window STFT) and the backward is a dot product.
-        jvp = USE_JVP and ctx.needs_input_grad[1] and not ctx.needs_input_grad[0] and _jvp_supported(lib, geo.n_fft)
+        # (decided by dmel(): grad mode is always off in here and needs_input_grad mirrors requires_grad even under
+        # torch.no_grad(), so validation / inference passes would otherwise pay for the forward-mode kernel)
         dy = torch.empty_like(y) if jvp else None
         bank_ref = bank.ref() if bank is not None else None
         with _on_device(dev):
@@ -203,7 +204,7 @@ class DmelFunction(torch.autograd.Function):
                 g_lambd = g_lambd.reshape(ctx.lambd_shape)
             if ctx.lambd_dtype != torch.float32:
                 g_lambd = g_lambd.to(ctx.lambd_dtype)
-        return grad_x, g_lambd, None, None, None, None, None, None
+        return grad_x, g_lambd, None, None, None, None, None, None, None
 
 
 def workspace_energy(ws: torch.Tensor) -> torch.Tensor:
@@ -302,7 +303,10 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
                 _affine_cache[akey] = abank
         bank = abank
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-    y = DmelFunction.apply(x, lambd, ws, geo, bank, eps, flags, lam_value)
+    # forward-mode kernel only when a backward can follow: grad mode on, lambd trains, x does not
+    jvp = (USE_JVP and torch.is_grad_enabled() and lambd.requires_grad and not x.requires_grad
+           and _jvp_supported(_lib.load(), geo.n_fft))
+    y = DmelFunction.apply(x, lambd, ws, geo, bank, eps, flags, lam_value, jvp)
     if return_workspace:
         return y, ws
     return (y, workspace_energy(ws)) if return_energy else y

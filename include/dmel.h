@@ -196,7 +196,8 @@ DMEL_API int dmel_backward_f32(const void* x, int64_t batch, int64_t n_points, i
  * device memory, maps every peer's buffer into its own address space (CUDA IPC) and passes the `world` base
  * pointers (its own at index `rank`) as a DEVICE array of 64-bit addresses.  `value` (device, 1 x fp32) is replaced
  * by the sum, bit-identical on all ranks (summed in rank order).  Stream-ordered, graph-capturable; every rank must
- * make the same sequence of calls.  On a peer timeout (~2 s) the result is NaN and word [4*world+1] of the
+ * make the same sequence of calls.  Like any collective it waits for its peers; the wait is bounded by
+ * DMEL_PEER_TIMEOUT_S (environment, default 1800 s): on expiry the result is NaN and word [4*world+1] of the
  * rank's buffer is set to 1.  dist.py (PeerRing) is the host side; NCCL remains the fallback.                     */
 DMEL_API size_t dmel_peer_buffer_bytes(int32_t world);
 /* The symmetric buffers are whole cudaMalloc allocations (that is what a CUDA IPC handle names), owned by the
