@@ -100,7 +100,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with open(stamp) as fh:
             if fh.read().strip() == want:
                 return LIB_PATH
-    proc = subprocess.run(["make", "-B", "-C", CSRC_DIR], capture_output=True, text=True)
+    # the tiled-kernel instantiations are separate objects: build them in parallel
+    proc = subprocess.run(["make", "-B", f"-j{max(1, os.cpu_count() or 1)}", "-C", CSRC_DIR], capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         print(proc.stdout)
         print(proc.stderr)

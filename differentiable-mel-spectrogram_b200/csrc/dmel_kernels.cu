@@ -1,5 +1,6 @@
-// dmel_kernels.cu — fused DMEL forward / backward kernels for sm_100a and their C ABI (one translation unit:
-// this file holds the host-side planner, dispatch and the extern "C" entry points; the device code is in
+// dmel_kernels.cu — fused DMEL forward / backward kernels for sm_100a and their C ABI.  This file holds the host-side
+// planner, the dispatch and the extern "C" entry points; the tiled kernels are instantiated in inst_tiled.cu (one
+// object per transform length and direction, built in parallel); the device code is in
 //   fft_device.cuh          in-register / shared-memory FFT building blocks
 //   dmel_common.cuh         workspace + geometry structs, reductions, shared-memory layout, cp.async staging
 //   dmel_small_kernels.cuh  prep, zero-init, finalize
@@ -48,9 +49,10 @@
 #include "fft_device.cuh"
 
 #include "dmel_common.cuh"
+#include "dmel_host.cuh"
 #include "dmel_small_kernels.cuh"
-#include "dmel_tiled_kernels.cuh"
-#include "dmel_tiled2_kernels.cuh"
+#include "dmel_tiled_kernels.cuh"   // shared-memory layouts and plan constants for the planner; the tiled kernels
+#include "dmel_tiled2_kernels.cuh"  // themselves are instantiated in inst_tiled.cu
 #include "dmel_big_kernels.cuh"
 #include "dmel_dft_kernels.cuh"
 
@@ -76,7 +78,6 @@ static long long peer_timeout_cycles() {
     return cycles;
 }
 #define PEER_TIMEOUT_CYCLES peer_timeout_cycles()
-constexpr int NUM_SMS = 148;
 
 template <int L> static PlanDesc plan_desc_of() {
     PlanDesc d;
@@ -117,7 +118,7 @@ static FftInfo fft_info(int n_fft) {
 static bool has_fft_plan(int n_fft) { return fft_info(n_fft).ok; }
 
 // second-generation tiled kernels (fft_core.cuh / dmel_tiled2_kernels.cuh): n_fft 256..4096, 16 points per thread.
-// DMEL_V1=1 in the environment keeps the first generation (A/B measurements).
+// (the first generation, dmel_tiled_kernels.cuh, still serves n_fft 128)
 template <int L> static PlanDesc plan2_desc_of() {
     PlanDesc d;
     d.np = v2::Fft<L>::NP;
@@ -132,8 +133,6 @@ struct Fft2Info {
 };
 static Fft2Info fft2_info(int n_fft) {
     Fft2Info f{};
-    static const bool v1 = getenv("DMEL_V1") != nullptr && atoi(getenv("DMEL_V1")) != 0;
-    if (v1) return f;
     switch (n_fft) {
 #define DMEL_FFT2_CASE(LL, NGA, NGB)                                                                             \
     case LL: f.ok = true; f.gt = v2::Fft<LL>::GT; f.tw_smem = v2::Fft<LL>::TW_SMEM; f.buf = v2::Fft<LL>::BUF;      \
@@ -149,14 +148,6 @@ static Fft2Info fft2_info(int n_fft) {
     return f;
 }
 
-struct LaunchPlan {
-    int path;  // 0 FFT, 1 direct DFT, 2 big FFT
-    int gen;   // tiled FFT path: 1 first-generation kernels, 2 second generation
-    int lookahead;
-    int NG, SF, TT, span, sub_span, tiles_per_clip, threads;
-    int csr_ints, csr_floats;
-    size_t smem;
-};
 
 // second generation: forward keeps an [M][TT+1] tile (two planes for the JVP forward) and int2-per-mel records + the
 // mel-major weights; backward keeps (M+1) x (TT+2) tiles of dL/dy and y (doubled by the look-ahead) and one 16-byte
@@ -305,233 +296,9 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
     return DMEL_ERR_SMEM_EXCEEDED;
 }
 
-// ---- optional instrumentation for bench.py: launch counter + per-kernel CUDA-event timing.
-// Off by default; when on, every main-kernel launch is bracketed by a pair of events recorded on
-// the launching stream (no synchronisation until dmel_profile_read).
-enum { PROF_PREP = 0, PROF_FWD = 1, PROF_BWD = 2, PROF_FINALIZE = 3, PROF_ZERO = 4, PROF_KINDS = 5 };
-static std::atomic<long long> g_launches[PROF_KINDS];
-struct ProfState {
-    bool on = false;
-    std::vector<cudaEvent_t> ev[PROF_KINDS];  // start/stop pairs
-};
-static thread_local ProfState t_prof;
-
-struct ProfScope {
-    int kind;
-    cudaStream_t st;
-    ProfScope(int k, cudaStream_t s) : kind(k), st(s) {
-        g_launches[kind].fetch_add(1, std::memory_order_relaxed);
-        if (t_prof.on) {
-            cudaEvent_t e;
-            cudaEventCreate(&e);
-            cudaEventRecord(e, st);
-            t_prof.ev[kind].push_back(e);
-        }
-    }
-    ~ProfScope() {
-        if (t_prof.on) {
-            cudaEvent_t e;
-            cudaEventCreate(&e);
-            cudaEventRecord(e, st);
-            t_prof.ev[kind].push_back(e);
-        }
-    }
-};
-
-static int check_launch(const char* what) {
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        fprintf(stderr, "[dmel] %s: %s\n", what, cudaGetErrorString(e));
-        return DMEL_ERR_LAUNCH_FAILED;
-    }
-    return DMEL_OK;
-}
-
-// Per-kernel launch state that does not change between calls: the opt-in to > 48 KB of dynamic shared memory and the
-// occupancy behind the persistent grid.  Both are properties of (kernel, device); they are looked up once per kernel
-// instantiation and device instead of on every launch (the host cost of a call is two launches' worth of driver work).
-constexpr int MAX_DEVICES = 64;
-struct KernelCache {
-    std::atomic<size_t> smem_ok[MAX_DEVICES];     // largest dynamic shared memory size already opted in
-    std::atomic<uint64_t> occ[MAX_DEVICES];       // (threads << 40 | smem << 8 | per_sm) of the last occupancy query
-    std::atomic<int> sms[MAX_DEVICES];
-};
-
-static int current_device() {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) {
-        (void)cudaGetLastError();
-        dev = 0;
-    }
-    return dev;
-}
-
-template <typename K>
-static int set_smem(K kernel, size_t smem, KernelCache* kc = nullptr) {
-    if (smem > 48 * 1024) {
-        const int dev = current_device();
-        if (kc && dev < MAX_DEVICES && kc->smem_ok[dev].load(std::memory_order_relaxed) >= smem) return DMEL_OK;
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) {
-            fprintf(stderr, "[dmel] cudaFuncSetAttribute(%zu): %s\n", smem, cudaGetErrorString(e));
-            (void)cudaGetLastError();
-            return DMEL_ERR_LAUNCH_FAILED;
-        }
-        if (kc && dev < MAX_DEVICES) kc->smem_ok[dev].store(smem, std::memory_order_relaxed);
-    }
-    return DMEL_OK;
-}
-
-// persistent launch: one resident wave of CTAs (occupancy x SM count), each walking tiles with stride gridDim
-template <typename K>
-static unsigned persistent_grid(K kernel, const LaunchPlan& lp, int64_t total_tiles, KernelCache* kc = nullptr) {
-    const int dev = current_device();
-    const uint64_t key = (uint64_t(lp.threads) << 40) | (uint64_t(lp.smem) << 8);
-    int per_sm = 0, sms = 0;
-    if (kc && dev < MAX_DEVICES) {
-        const uint64_t c = kc->occ[dev].load(std::memory_order_relaxed);
-        if ((c & ~uint64_t(0xff)) == key && (c & 0xff) != 0) {
-            per_sm = int(c & 0xff);
-            sms = kc->sms[dev].load(std::memory_order_relaxed);
-        }
-    }
-    if (per_sm < 1 || sms < 1) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, lp.threads, lp.smem) != cudaSuccess || per_sm < 1) {
-            (void)cudaGetLastError();
-            per_sm = 1;
-        }
-        sms = NUM_SMS;
-        int v = 0;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
-        if (kc && dev < MAX_DEVICES) {
-            kc->sms[dev].store(sms, std::memory_order_relaxed);
-            kc->occ[dev].store(key | uint64_t(per_sm & 0xff), std::memory_order_relaxed);
-        }
-    }
-    const int64_t cap = int64_t(per_sm) * sms;
-    return unsigned(std::min<int64_t>(total_tiles, cap));
-}
-
-template <int L, int NG, bool SPEC, bool JVP>
-static int launch_fwd_t(const float* x, float* y, float* dy, const Geom& g, const MelDev& mel, const WsView& ws,
-                        const LaunchPlan& lp, cudaStream_t st) {
-    static KernelCache kc;     // one per instantiation
-    int rc;
-    if ((rc = set_smem(dmel_fwd_kernel<L, NG, SPEC, JVP>, lp.smem, &kc))) return rc;
-    const unsigned grid = persistent_grid(dmel_fwd_kernel<L, NG, SPEC, JVP>, lp, int64_t(g.B) * g.tiles_per_clip, &kc);
-    ProfScope prof(PROF_FWD, st);
-    dmel_fwd_kernel<L, NG, SPEC, JVP><<<grid, lp.threads, lp.smem, st>>>(x, y, dy, g, mel, ws.win, ws.tw, ws.means, ws.hdr);
-    return check_launch("dmel_fwd_kernel");
-}
-
-template <int L, int NG, bool SPEC, bool NEED_DX>
-static int launch_bwd_t(const float* x, const float* y, const float* gy, float* dx, const Geom& g, const MelDev& mel,
-                        const WsView& ws, const LaunchPlan& lp, cudaStream_t st) {
-    static KernelCache kc;     // one per instantiation
-    int rc;
-    if ((rc = set_smem(dmel_bwd_kernel<L, NG, SPEC, NEED_DX>, lp.smem, &kc))) return rc;
-    const unsigned grid = persistent_grid(dmel_bwd_kernel<L, NG, SPEC, NEED_DX>, lp, int64_t(g.B) * g.tiles_per_clip, &kc);
-    ProfScope prof(PROF_BWD, st);
-    dmel_bwd_kernel<L, NG, SPEC, NEED_DX>
-        <<<grid, lp.threads, lp.smem, st>>>(x, y, gy, dx, g, mel, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
-    return check_launch("dmel_bwd_kernel");
-}
-
-template <int L, int NG>
-static int launch_fwd(const float* x, float* y, float* dy, const Geom& g, const MelDev& mel, bool spec, const WsView& ws,
-                      const LaunchPlan& lp, cudaStream_t st) {
-    if (dy) {
-        return spec ? launch_fwd_t<L, NG, true, true>(x, y, dy, g, mel, ws, lp, st)
-                    : launch_fwd_t<L, NG, false, true>(x, y, dy, g, mel, ws, lp, st);
-    }
-    return spec ? launch_fwd_t<L, NG, true, false>(x, y, nullptr, g, mel, ws, lp, st)
-                : launch_fwd_t<L, NG, false, false>(x, y, nullptr, g, mel, ws, lp, st);
-}
-
-template <int L, int NG>
-static int launch_bwd(const float* x, const float* y, const float* gy, float* dx, const Geom& g, const MelDev& mel,
-                      bool spec, const WsView& ws, const LaunchPlan& lp, cudaStream_t st) {
-    if (spec) {
-        return dx ? launch_bwd_t<L, NG, true, true>(x, y, gy, dx, g, mel, ws, lp, st)
-                  : launch_bwd_t<L, NG, true, false>(x, y, gy, dx, g, mel, ws, lp, st);
-    }
-    return dx ? launch_bwd_t<L, NG, false, true>(x, y, gy, dx, g, mel, ws, lp, st)
-              : launch_bwd_t<L, NG, false, false>(x, y, gy, dx, g, mel, ws, lp, st);
-}
-
-// ---- second generation
-template <int L, int NG, bool SPEC, bool JVP>
-static int launch_fwd2_t(const void* x, float* y, float* dy, const Geom& g, const MelDev& mel, const WsView& ws,
-                         const LaunchPlan& lp, cudaStream_t st) {
-    static KernelCache kc;     // one per instantiation
-    int rc;
-    if ((rc = set_smem(v2::dmel2_fwd_kernel<L, NG, SPEC, JVP>, lp.smem, &kc))) return rc;
-    const unsigned grid = persistent_grid(v2::dmel2_fwd_kernel<L, NG, SPEC, JVP>, lp, int64_t(g.B) * g.tiles_per_clip, &kc);
-    ProfScope prof(PROF_FWD, st);
-    v2::dmel2_fwd_kernel<L, NG, SPEC, JVP><<<grid, lp.threads, lp.smem, st>>>(x, y, dy, g, mel, ws.win, ws.tw, ws.means, ws.hdr);
-    return check_launch("dmel2_fwd_kernel");
-}
-
-template <int L, int NG, bool SPEC, bool NEED_DX>
-static int launch_bwd2_t(const void* x, const float* y, const float* gy, float* dx, const Geom& g, const MelDev& mel,
-                         const WsView& ws, const LaunchPlan& lp, cudaStream_t st) {
-    static KernelCache kc;     // one per instantiation
-    int rc;
-    if ((rc = set_smem(v2::dmel2_bwd_kernel<L, NG, SPEC, NEED_DX>, lp.smem, &kc))) return rc;
-    const unsigned grid = persistent_grid(v2::dmel2_bwd_kernel<L, NG, SPEC, NEED_DX>, lp, int64_t(g.B) * g.tiles_per_clip, &kc);
-    ProfScope prof(PROF_BWD, st);
-    v2::dmel2_bwd_kernel<L, NG, SPEC, NEED_DX>
-        <<<grid, lp.threads, lp.smem, st>>>(x, y, gy, dx, g, mel, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
-    return check_launch("dmel2_bwd_kernel");
-}
-
-template <int L, int NG>
-static int launch_fwd2(const void* x, float* y, float* dy, const Geom& g, const MelDev& mel, bool spec, const WsView& ws,
-                       const LaunchPlan& lp, cudaStream_t st) {
-    if (dy) {
-        return spec ? launch_fwd2_t<L, NG, true, true>(x, y, dy, g, mel, ws, lp, st)
-                    : launch_fwd2_t<L, NG, false, true>(x, y, dy, g, mel, ws, lp, st);
-    }
-    return spec ? launch_fwd2_t<L, NG, true, false>(x, y, nullptr, g, mel, ws, lp, st)
-                : launch_fwd2_t<L, NG, false, false>(x, y, nullptr, g, mel, ws, lp, st);
-}
-
-template <int L, int NG>
-static int launch_bwd2(const void* x, const float* y, const float* gy, float* dx, const Geom& g, const MelDev& mel,
-                       bool spec, const WsView& ws, const LaunchPlan& lp, cudaStream_t st) {
-    if (spec) {
-        return dx ? launch_bwd2_t<L, NG, true, true>(x, y, gy, dx, g, mel, ws, lp, st)
-                  : launch_bwd2_t<L, NG, true, false>(x, y, gy, dx, g, mel, ws, lp, st);
-    }
-    return dx ? launch_bwd2_t<L, NG, false, true>(x, y, gy, dx, g, mel, ws, lp, st)
-              : launch_bwd2_t<L, NG, false, false>(x, y, gy, dx, g, mel, ws, lp, st);
-}
-
-#ifdef DMEL_FAST_BUILD
-// development builds: only the shapes of the benchmarked workloads (seconds instead of minutes to compile)
-#define DMEL_DISPATCH2(n_fft, ng, CALL)                                  \
-    switch ((n_fft) * 16 + (ng)) {                                       \
-        case 512 * 16 + 4: rc = CALL(512, 4); break;                     \
-        case 1024 * 16 + 4: rc = CALL(1024, 4); break;                   \
-        case 1024 * 16 + 2: rc = CALL(1024, 2); break;                   \
-        case 2048 * 16 + 1: rc = CALL(2048, 1); break;                   \
-        default: rc = DMEL_ERR_UNSUPPORTED_NFFT;                         \
-    }
-#else
-#define DMEL_DISPATCH2(n_fft, ng, CALL)                                  \
-    switch ((n_fft) * 16 + (ng)) {                                       \
-        case 256 * 16 + 8: rc = CALL(256, 8); break;                     \
-        case 256 * 16 + 4: rc = CALL(256, 4); break;                     \
-        case 512 * 16 + 8: rc = CALL(512, 8); break;                     \
-        case 512 * 16 + 4: rc = CALL(512, 4); break;                     \
-        case 1024 * 16 + 4: rc = CALL(1024, 4); break;                   \
-        case 1024 * 16 + 2: rc = CALL(1024, 2); break;                   \
-        case 2048 * 16 + 2: rc = CALL(2048, 2); break;                   \
-        case 2048 * 16 + 1: rc = CALL(2048, 1); break;                   \
-        case 4096 * 16 + 1: rc = CALL(4096, 1); break;                   \
-        default: rc = DMEL_ERR_UNSUPPORTED_NFFT;                         \
-    }
-#endif
+// launch instrumentation state (declared in dmel_host.cuh, shared with the inst_tiled.cu translation units)
+std::atomic<long long> g_launches[PROF_KINDS];
+thread_local ProfState t_prof;
 
 template <int L>
 static int launch_big_fwd(const float* x, float* y, const Geom& g, const MelDev& mel, bool spec, const WsView& ws,
@@ -571,27 +338,6 @@ static int launch_big_bwd(const float* x, const float* y, const float* gy, float
     return dx ? launch_big_bwd_t<L, false, true>(x, y, gy, dx, g, mel, ws, lp, st)
               : launch_big_bwd_t<L, false, false>(x, y, gy, dx, g, mel, ws, lp, st);
 }
-
-// (n_fft, NG) -> instantiation; the NG values must match fft_info()
-#ifdef DMEL_FAST_BUILD
-#define DMEL_DISPATCH(n_fft, ng, CALL) rc = DMEL_ERR_UNSUPPORTED_NFFT;
-#else
-#define DMEL_DISPATCH(n_fft, ng, CALL)                                   \
-    switch ((n_fft) * 16 + (ng)) {                                       \
-        case 128 * 16 + 8: rc = CALL(128, 8); break;                     \
-        case 128 * 16 + 4: rc = CALL(128, 4); break;                     \
-        case 256 * 16 + 8: rc = CALL(256, 8); break;                     \
-        case 256 * 16 + 4: rc = CALL(256, 4); break;                     \
-        case 512 * 16 + 8: rc = CALL(512, 8); break;                     \
-        case 512 * 16 + 4: rc = CALL(512, 4); break;                     \
-        case 1024 * 16 + 4: rc = CALL(1024, 4); break;                   \
-        case 1024 * 16 + 2: rc = CALL(1024, 2); break;                   \
-        case 2048 * 16 + 2: rc = CALL(2048, 2); break;                   \
-        case 2048 * 16 + 1: rc = CALL(2048, 1); break;                   \
-        case 4096 * 16 + 1: rc = CALL(4096, 1); break;                   \
-        default: rc = DMEL_ERR_UNSUPPORTED_NFFT;                         \
-    }
-#endif
 
 static int validate(const void* x, int64_t B, int64_t N, int64_t stride, int32_t win, int32_t n_fft, int32_t hop,
                     int32_t n_mels, const dmel_melbank* bank, void* ws, size_t ws_bytes_in) {
@@ -795,14 +541,15 @@ static int forward_impl(const void* x, int64_t batch, int64_t n_points, int64_t 
     }
 #endif
     if (gen2) {
-#define CALL_FWD2(LL, NGG) launch_fwd2<LL, NGG>(x, y, dy, g, mel, spec, ws, lp, st)
-        DMEL_DISPATCH2(n_fft, lp.NG, CALL_FWD2)
-#undef CALL_FWD2
+        switch (n_fft) {
+#define DMEL_CASE(LL) case LL: rc = launch_tiled2_fwd_##LL(lp.NG, x, y, dy, g, mel, spec, ws, lp, st); break;
+            DMEL_CASE(256) DMEL_CASE(512) DMEL_CASE(1024) DMEL_CASE(2048) DMEL_CASE(4096)
+#undef DMEL_CASE
+            default: rc = DMEL_ERR_UNSUPPORTED_NFFT;
+        }
         return rc;
     }
-#define CALL_FWD(LL, NGG) launch_fwd<LL, NGG>(xf, y, dy, g, mel, spec, ws, lp, st)
-    DMEL_DISPATCH(n_fft, lp.NG, CALL_FWD)
-#undef CALL_FWD
+    rc = launch_tiled1_fwd(n_fft, lp.NG, xf, y, dy, g, mel, spec, ws, lp, st);
     return rc;
 }
 
@@ -935,14 +682,15 @@ static int backward_impl(const void* x, int64_t batch, int64_t n_points, int64_t
         if (rc) return rc;
 #endif
     } else if (gen2) {
-#define CALL_BWD2(LL, NGG) launch_bwd2<LL, NGG>(x, y, grad_y, grad_x, g, mel, spec, ws, lp, st)
-        DMEL_DISPATCH2(n_fft, lp.NG, CALL_BWD2)
-#undef CALL_BWD2
+        switch (n_fft) {
+#define DMEL_CASE(LL) case LL: rc = launch_tiled2_bwd_##LL(lp.NG, x, y, grad_y, grad_x, g, mel, spec, ws, lp, st); break;
+            DMEL_CASE(256) DMEL_CASE(512) DMEL_CASE(1024) DMEL_CASE(2048) DMEL_CASE(4096)
+#undef DMEL_CASE
+            default: rc = DMEL_ERR_UNSUPPORTED_NFFT;
+        }
         if (rc) return rc;
     } else {
-#define CALL_BWD(LL, NGG) launch_bwd<LL, NGG>(xf, y, grad_y, grad_x, g, mel, spec, ws, lp, st)
-        DMEL_DISPATCH(n_fft, lp.NG, CALL_BWD)
-#undef CALL_BWD
+        rc = launch_tiled1_bwd(n_fft, lp.NG, xf, y, grad_y, grad_x, g, mel, spec, ws, lp, st);
         if (rc) return rc;
     }
     const float sign = lambda > 0.f ? 1.f : (lambda < 0.f ? -1.f : 0.f);

@@ -251,10 +251,10 @@ dmel2_fwd_kernel(const void* __restrict__ x, float* __restrict__ y, float* __res
             for (int q = 0; q < 16; ++q) {
                 const float a = xa[GT * q];
                 if (JVP) {
-                    z[q] = make_float2(a * wh[q], a * whd[q]);
+                    z[q] = px::mul2(px::bc(a), make_float2(wh[q], whd[q]));
                 } else {
                     const float c = xb[GT * q];
-                    z[q] = make_float2(a * wh[q], c * wh[q]);
+                    z[q] = px::mul2(make_float2(a, c), px::bc(wh[q]));
                 }
             }
 #ifndef DMEL2_EXP_NOFFT
@@ -271,11 +271,17 @@ dmel2_fwd_kernel(const void* __restrict__ x, float* __restrict__ y, float* __res
             const float2* lp = buf + L - gtid;
             float* tcol = tile + gtid * TS + f;
             auto split = [&](const float2 z1, const float2 z2, float& pa, float& pb) {
-                const float ar = z1.x + z2.x, ai = z1.y - z2.y;
-                const float br = z1.y + z2.y, bi = z2.x - z1.x;
+                // X_a = (ar, ai), X_b = (br, bi):  (ar, br) = z1 + z2,  (-bi, ai) = z1 - z2
+                const float2 sm = px::add2(z1, z2), df = px::sub2(z1, z2);
                 // pair: both powers.  JVP: (ar,ai) = X, (br,bi) = X' -> P = |X|^2, dP/d|lambda| = 2 Re(conj(X) X')
-                pa = fmaf(ar, ar, ai * ai);
-                pb = JVP ? 2.f * fmaf(ar, br, ai * bi) : fmaf(br, br, bi * bi);
+                if (JVP) {
+                    pa = fmaf(sm.x, sm.x, df.y * df.y);
+                    pb = 2.f * fmaf(sm.x, sm.y, -df.y * df.x);
+                } else {
+                    const float2 p = px::fma2(px::swap(df), px::swap(df), px::mul2(sm, sm));
+                    pa = p.x;
+                    pb = p.y;
+                }
             };
             if (SPEC) {
 #pragma unroll
@@ -601,7 +607,7 @@ dmel2_bwd_kernel(const void* __restrict__ x, const float* __restrict__ y, const 
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const float a = xa[GT * q], c = xb[GT * q];
-                z[q] = make_float2(a * wh[q], c * wh[q]);
+                z[q] = px::mul2(make_float2(a, c), px::bc(wh[q]));
             }
             // the forward and the inverse transform share ONE copy of the FFT code (rolled two-trip loop): the
             // unrolled butterflies are most of the kernel's instruction footprint
@@ -639,8 +645,9 @@ dmel2_bwd_kernel(const void* __restrict__ x, const float* __restrict__ y, const 
                     const float2 g0 = *reinterpret_cast<const float2*>(r0);
                     const float2 g1 = *reinterpret_cast<const float2*>(r0 + TS);
                     const float w0 = __int_as_float(mt.y), w1 = __int_as_float(mt.z);
-                    ga = fmaf(w1, g1.x, w0 * g0.x);
-                    gb = fmaf(w1, g1.y, w0 * g0.y);
+                    const float2 gab = px::fma2(px::bc(w1), g1, px::mul2(px::bc(w0), g0));
+                    ga = gab.x;
+                    gb = gab.y;
                     if (mt.w) {   // banks with more than two taps per bin (not the triangular HTK bank): slow path
                         const int o0 = __ldg(mel.bin_off + k);
                         const float e = (k == 0 || k == L / 2) ? 2.f : 1.f;
@@ -659,8 +666,9 @@ dmel2_bwd_kernel(const void* __restrict__ x, const float* __restrict__ y, const 
                 bin_grad(gtid + GT * q, ga, gb);
                 const float s = ga + gb, d = ga - gb;
                 const float2 z1 = z[q], z2 = lp[-GT * q];
-                z[q] = make_float2(fmaf(s, z1.x, d * z2.x), fmaf(-s, z1.y, d * z2.y));
-                lp[-GT * q] = make_float2(fmaf(s, z2.x, d * z1.x), fmaf(-s, z2.y, d * z1.y));
+                const float2 sc = make_float2(s, -s);
+                z[q] = px::fma2(sc, z1, px::mul2(px::bc(d), z2));
+                lp[-GT * q] = px::fma2(sc, z2, px::mul2(px::bc(d), z1));
             }
             if (gtid == 0) {   // bin L/2 pairs with itself
                 float ga, gb;

@@ -22,6 +22,7 @@
 
 #include <type_traits>
 
+#include "f32x2.cuh"
 #include "fft_device.cuh"   // float2 helpers, RegDft<2/4>, group_sync
 
 namespace dmel {
@@ -46,39 +47,36 @@ template <int GT> __device__ __forceinline__ int group_sync_arg(int grp) {
 // radix butterflies, forward sign, natural order in/out
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
-    const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2);
-    const float2 s13 = cadd(a1, a3), d13 = csub(a1, a3);
-    a0 = cadd(s02, s13);
-    a2 = csub(s02, s13);
-    // d13 * (-i) = (d13.y, -d13.x)
-    a1 = make_float2(d02.x + d13.y, d02.y - d13.x);
-    a3 = make_float2(d02.x - d13.y, d02.y + d13.x);
+    const float2 s02 = px::add2(a0, a2), d02 = px::sub2(a0, a2);
+    const float2 s13 = px::add2(a1, a3), d13 = px::sub2(a1, a3);
+    a0 = px::add2(s02, s13);
+    a2 = px::sub2(s02, s13);
+    a1 = px::add_mi(d02, d13);   // d02 + d13*(-i)
+    a3 = px::sub_mi(d02, d13);
 }
 
 // e +- o*W8^1 = e +- C*(o.x+o.y, o.y-o.x);   e +- o*W8^3 = e +- C*(o.y-o.x, -(o.x+o.y))
 __device__ __forceinline__ void bf_w8_1(const float2 e, const float2 o, float2& lo, float2& hi) {
     constexpr float C = 0.70710678118654752440f;
-    const float s = o.x + o.y, d = o.y - o.x;
-    lo = make_float2(fmaf(C, s, e.x), fmaf(C, d, e.y));
-    hi = make_float2(fmaf(-C, s, e.x), fmaf(-C, d, e.y));
+    const float2 u = px::fma2(px::swap(o), px::pm(), o);
+    lo = px::fma2(px::bc(C), u, e);
+    hi = px::fma2(px::bc(-C), u, e);
 }
 __device__ __forceinline__ void bf_w8_3(const float2 e, const float2 o, float2& lo, float2& hi) {
     constexpr float C = 0.70710678118654752440f;
-    const float s = o.x + o.y, d = o.y - o.x;
-    lo = make_float2(fmaf(C, d, e.x), fmaf(-C, s, e.y));
-    hi = make_float2(fmaf(-C, d, e.x), fmaf(C, s, e.y));
+    const float2 u = px::fma2(px::swap(o), px::pm(), px::neg(o));
+    lo = px::fma2(px::bc(C), u, e);
+    hi = px::fma2(px::bc(-C), u, e);
 }
 // e +- o*(-i)
 __device__ __forceinline__ void bf_mi(const float2 e, const float2 o, float2& lo, float2& hi) {
-    lo = make_float2(e.x + o.y, e.y - o.x);
-    hi = make_float2(e.x - o.y, e.y + o.x);
+    lo = px::add_mi(e, o);
+    hi = px::sub_mi(e, o);
 }
 // e +- o*(wr + i*wi), compile-time constant
 __device__ __forceinline__ void bf_w(const float2 e, const float2 o, const float wr, const float wi, float2& lo,
                                      float2& hi) {
-    const float tx = fmaf(o.x, wr, -o.y * wi), ty = fmaf(o.x, wi, o.y * wr);
-    lo = make_float2(e.x + tx, e.y + ty);
-    hi = make_float2(e.x - tx, e.y - ty);
+    px::bf_const(e, o, wr, wi, lo, hi);
 }
 
 __device__ __forceinline__ void dft8(float2 (&v)[8]) {
@@ -86,8 +84,8 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
     float2 o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
     dft4(e0, e1, e2, e3);
     dft4(o0, o1, o2, o3);
-    v[0] = cadd(e0, o0);
-    v[4] = csub(e0, o0);
+    v[0] = px::add2(e0, o0);
+    v[4] = px::sub2(e0, o0);
     bf_w8_1(e1, o1, v[1], v[5]);
     bf_mi(e2, o2, v[2], v[6]);
     bf_w8_3(e3, o3, v[3], v[7]);
@@ -101,8 +99,8 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
     for (int i = 0; i < 8; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
     dft8(e);
     dft8(o);
-    v[0] = cadd(e[0], o[0]);
-    v[8] = csub(e[0], o[0]);
+    v[0] = px::add2(e[0], o[0]);
+    v[8] = px::sub2(e[0], o[0]);
     bf_w(e[1], o[1], C1, -S1, v[1], v[9]);
     bf_w8_1(e[2], o[2], v[2], v[10]);
     bf_w(e[3], o[3], S1, -C1, v[3], v[11]);
@@ -117,18 +115,16 @@ template <int M> __device__ __forceinline__ float2 mul_w16(const float2 v) {
     constexpr float C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f, C2 = 0.70710678118654752440f;
     constexpr int m = M & 15;
     if constexpr (m == 0) return v;
-    else if constexpr (m == 4) return make_float2(v.y, -v.x);
-    else if constexpr (m == 8) return make_float2(-v.x, -v.y);
-    else if constexpr (m == 12) return make_float2(-v.y, v.x);
-    else if constexpr (m == 2) return make_float2(C2 * (v.x + v.y), C2 * (v.y - v.x));
-    else if constexpr (m == 6) return make_float2(C2 * (v.y - v.x), -C2 * (v.x + v.y));
-    else if constexpr (m == 10) return make_float2(-C2 * (v.x + v.y), C2 * (v.x - v.y));
-    else if constexpr (m == 14) return make_float2(C2 * (v.x - v.y), C2 * (v.x + v.y));
+    else if constexpr (m == 4) return px::mul_mi(v);
+    else if constexpr (m == 8) return px::neg(v);
+    else if constexpr (m == 12) return px::neg(px::mul_mi(v));
     else {
         // (wr, wi) = (cos, -sin)(2*pi*m/16)
-        constexpr float wr = (m == 1 || m == 15) ? C1 : (m == 3 || m == 13) ? S1 : (m == 5 || m == 11) ? -S1 : -C1;
-        constexpr float wi = (m == 1 || m == 7) ? -S1 : (m == 3 || m == 5) ? -C1 : (m == 9 || m == 15) ? S1 : C1;
-        return make_float2(fmaf(v.x, wr, -v.y * wi), fmaf(v.x, wi, v.y * wr));
+        constexpr float wr = (m == 1 || m == 15) ? C1 : (m == 2 || m == 14) ? C2 : (m == 3 || m == 13) ? S1
+                           : (m == 5 || m == 11) ? -S1 : (m == 6 || m == 10) ? -C2 : -C1;
+        constexpr float wi = (m == 1 || m == 7) ? -S1 : (m == 2 || m == 6) ? -C2 : (m == 3 || m == 5) ? -C1
+                           : (m == 9 || m == 15) ? S1 : (m == 10 || m == 14) ? C2 : C1;
+        return px::cmul_const(v, wr, wi);
     }
 }
 
@@ -143,7 +139,7 @@ template <int R> __device__ __forceinline__ void dftR(float2 (&v)[R]) {
     if constexpr (R == 16) dft16(v);
     else if constexpr (R == 8) dft8(v);
     else if constexpr (R == 4) dft4(v[0], v[1], v[2], v[3]);
-    else if constexpr (R == 2) { const float2 a = v[0], b = v[1]; v[0] = cadd(a, b); v[1] = csub(a, b); }
+    else if constexpr (R == 2) { const float2 a = v[0], b = v[1]; v[0] = px::add2(a, b); v[1] = px::sub2(a, b); }
 }
 
 // ----------------------------------------------------------------------------
@@ -232,8 +228,8 @@ template <int L> struct Fft {
             for (int r = 0; r < R1; ++r) t[r] = c.g[padded(i * GT + r * S1)];
 #pragma unroll
             for (int r = 1; r < R1; ++r) {
-                if constexpr (TW1_REGS) t[r] = cmul(t[r], c.tw1[r - 1]);
-                else t[r] = cmul(t[r], c.t1[(r - 1) * 16]);
+                if constexpr (TW1_REGS) t[r] = px::cmul(t[r], c.tw1[r - 1]);
+                else t[r] = px::cmul(t[r], c.t1[(r - 1) * 16]);
             }
             dftR<R1>(t);
             if constexpr (NP == 2) {
@@ -259,8 +255,8 @@ template <int L> struct Fft {
                 bs[1] = c.tw2b[0]; bs[2] = c.tw2b[1]; bs[3] = c.tw2b[2];
             } else if constexpr (TW2_REGS && R2 == 8) {
                 bs[1] = c.tw2b[0]; bs[2] = c.tw2b[1]; bs[4] = c.tw2b[2];
-                bs[3] = cmul(bs[1], bs[2]); bs[5] = cmul(bs[1], bs[4]);
-                bs[6] = cmul(bs[2], bs[4]); bs[7] = cmul(bs[3], bs[4]);
+                bs[3] = px::cmul(bs[1], bs[2]); bs[5] = px::cmul(bs[1], bs[4]);
+                bs[6] = px::cmul(bs[2], bs[4]); bs[7] = px::cmul(bs[3], bs[4]);
             }
             static_for<0, NB2>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
@@ -270,11 +266,11 @@ template <int L> struct Fft {
                 if constexpr (TW2_REGS) {
                     static_for<1, R2>([&](auto rc) {
                         constexpr int r = decltype(rc)::value;
-                        t[r] = cmul(mul_w16<i * r>(t[r]), bs[r]);
+                        t[r] = px::cmul(mul_w16<i * r>(t[r]), bs[r]);
                     });
                 } else {
 #pragma unroll
-                    for (int r = 1; r < R2; ++r) t[r] = cmul(t[r], c.t2[(r - 1) * NS2 + i * GT]);
+                    for (int r = 1; r < R2; ++r) t[r] = px::cmul(t[r], c.t2[(r - 1) * NS2 + i * GT]);
                 }
                 dftR<R2>(t);
 #pragma unroll

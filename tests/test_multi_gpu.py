@@ -24,6 +24,7 @@ def _worker(rank, world, port, ret):
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    ring = None
     try:
         ring = dm.PeerRing.create(dev)
         assert ring is not None, "peer ring self-test failed"
@@ -44,11 +45,15 @@ def _worker(rank, world, port, ret):
         torch.cuda.synchronize()
         assert not ring.timed_out()
         ret[rank] = out
-        ring.close()
     finally:
+        # orderly teardown (the order bench.py uses): drain the device, agree that nobody is still inside a ring
+        # kernel, unmap the peers' buffers, then take the process group down
         torch.cuda.synchronize()
         dist.barrier()
-        os._exit(0)
+        if ring is not None:
+            ring.close()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
