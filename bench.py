@@ -185,7 +185,8 @@ def cpu_port_rate(w, budget_s, threads):
     t0 = time.perf_counter()
     one_pass(x1, G1)
     per_clip = (time.perf_counter() - t0) / 2
-    n = int(max(2, min(w["B"], (budget_s / 3.0) / max(per_clip, 1e-6))))
+    mem_cap = int(1.5e9 / (T * (w["n_fft"] // 2 + 1) * 8 * 3))      # autograd graph of the sample stays ~1.5 GB
+    n = int(max(2, min(w["B"], (budget_s / 3.0) / max(per_clip, 1e-6), mem_cap)))
     x = torch.randn(n, w["N"], generator=g)
     G = torch.randn(n, 1, w["M"], T, generator=g)
     best, reps, t_start = float("inf"), 0, time.perf_counter()
@@ -211,8 +212,12 @@ def run_reference_arm(args, wname, w):
     g = torch.Generator().manual_seed(1234)
     # size the per-step sample so that (steps + warmup) steps end within ~2 minutes
     rate, _, _, per_clip = cpu_port_rate(w, 4.0, cores)
-    budget = 120.0 / max(1, args.steps + args.warmup)
-    n = int(max(1, min(w["B"], budget / per_clip)))
+    # ... and so that one step is a few seconds of work and its autograd graph (complex spectrogram + frames + power per
+    # clip, kept for the backward) stays under a GB: the per-sample loop's cost is linear in clips, so the rate does not
+    # depend on the sample size, but a sample that swaps would
+    budget = min(5.0, 100.0 / max(1, args.steps + args.warmup))
+    mem_cap = int(0.75e9 / (T * (w["n_fft"] // 2 + 1) * 8 * 3))
+    n = int(max(1, min(w["B"], budget / per_clip, mem_cap)))
     x = torch.randn(n, w["N"], generator=g)
     G = torch.randn(n, 1, w["M"], T, generator=g)
 
@@ -292,7 +297,8 @@ class Resident:
         self.dxs = [torch.empty(B, N, device=dev) for _ in range(R)]
         self.dls = [torch.zeros((), device=dev) for _ in range(R)]
         self.wss = [torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev) for _ in range(R)]
-        self.side = torch.cuda.Stream(dev) if (cx.world > 1 and collective == "side") else None
+        # the side branch exists whenever the ring does: collective_check exercises it whatever the timed mode is
+        self.side = torch.cuda.Stream(dev) if (cx.world > 1 and cx.ring is not None) else None
         self.graph = None
 
     def args_fwd(self, s, st):

@@ -140,7 +140,7 @@ static Fft2Info fft2_info(int n_fft) {
         DMEL_FFT2_CASE(256, 8, 4)
         DMEL_FFT2_CASE(512, 8, 4)
         DMEL_FFT2_CASE(1024, 4, 2)
-        DMEL_FFT2_CASE(2048, 2, 1)
+        DMEL_FFT2_CASE(2048, 4, 1)
         DMEL_FFT2_CASE(4096, 1, 1)
 #undef DMEL_FFT2_CASE
         default: break;
@@ -373,7 +373,7 @@ static MelDev mel_dev(const dmel_melbank* bank) {
 }
 
 static int run_prep(const void* x, int64_t B, int64_t N, int64_t stride, float lam_abs, int32_t win, int32_t n_fft,
-                    int32_t flags, const WsView& ws, cudaStream_t st, bool gen2) {
+                    int32_t flags, const WsView& ws, cudaStream_t st, bool gen2, const float* means_src = nullptr) {
     ProfScope prof(PROF_PREP, st);
     const int nseg = prep_segments(int(N));
     if ((B + 1) * int64_t(nseg) > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
@@ -388,7 +388,7 @@ static int run_prep(const void* x, int64_t B, int64_t N, int64_t stride, float l
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, dmel_prep_kernel, x, (long long)stride, int(B), int(N), lam_abs, int(win), int(n_fft),
-                       int(flags), ws, gen2 ? fft2_info(n_fft).desc : fft_info(n_fft).desc);
+                       int(flags), ws, gen2 ? fft2_info(n_fft).desc : fft_info(n_fft).desc, means_src);
     return check_launch("dmel_prep_kernel");
 }
 
@@ -499,7 +499,7 @@ static int row_alignment_ok(const void* x, int64_t stride, int dtype) {
 static int forward_impl(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
                         int32_t win_length, int32_t n_fft, int32_t hop, int32_t n_mels, const dmel_melbank* bank,
                         float log_eps, int32_t flags, float* y, float* dy, void* workspace, size_t workspace_bytes,
-                        void* cuda_stream) {
+                        void* cuda_stream, const float* means_src = nullptr) {
     if (!y) return DMEL_ERR_NULL_POINTER;
     int rc = validate(x, batch, n_points, x_row_stride, win_length, n_fft, hop, n_mels, bank, workspace, workspace_bytes);
     if (rc) return rc;
@@ -518,16 +518,13 @@ static int forward_impl(const void* x, int64_t batch, int64_t n_points, int64_t 
     const bool gen2 = lp.path == 0 && lp.gen == 2;
     WsView ws = ws_view(workspace, batch, n_fft);
     const MelDev mel = mel_dev(bank);
-    if ((rc = run_prep(x, batch, n_points, x_row_stride, fabsf(lambda), win_length, n_fft, flags, ws, st, gen2)))
+    if ((rc = run_prep(x, batch, n_points, x_row_stride, fabsf(lambda), win_length, n_fft, flags, ws, st, gen2, means_src)))
         return rc;
     Geom g = make_geom(batch, n_points, x_row_stride, n_fft, hop, rows, log_eps, lp);
     g.x_dtype = x_dtype;
     g.row_aligned = row_alignment_ok(x, x_row_stride, x_dtype);
     g.time_major = (flags & DMEL_FLAG_TIME_MAJOR) ? 1 : 0;
     const float* xf = static_cast<const float*>(x);
-#ifdef DMEL_FAST_BUILD
-    if (lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;
-#else
     if (lp.path == 1) {
         if ((rc = set_smem(dmel_dft_kernel<false, false>, lp.smem))) return rc;
         ProfScope prof(PROF_FWD, st);
@@ -539,7 +536,6 @@ static int forward_impl(const void* x, int64_t batch, int64_t n_points, int64_t 
         return n_fft == 8192 ? launch_big_fwd<8192>(xf, y, g, mel, spec, ws, lp, st)
                              : launch_big_fwd<16384>(xf, y, g, mel, spec, ws, lp, st);
     }
-#endif
     if (gen2) {
         switch (n_fft) {
 #define DMEL_CASE(LL) case LL: rc = launch_tiled2_fwd_##LL(lp.NG, x, y, dy, g, mel, spec, ws, lp, st); break;
@@ -568,6 +564,27 @@ extern "C" DMEL_API int dmel_forward_jvp_f32(const void* x, int64_t batch, int64
     if (!dy_dlambda) return DMEL_ERR_NULL_POINTER;
     return forward_impl(x, batch, n_points, x_row_stride, lambda, win_length, n_fft, hop, n_mels, bank, log_eps, flags, y,
                         dy_dlambda, workspace, workspace_bytes, cuda_stream);
+}
+
+extern "C" DMEL_API int dmel_forward_multi_f32(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
+                                               int32_t n_lambda, const float* lambdas, const int32_t* win_lengths,
+                                               const int32_t* n_ffts, int32_t hop, int32_t n_mels,
+                                               const dmel_melbank* const* banks, float log_eps, int32_t flags,
+                                               float* const* ys, void* const* workspaces, const size_t* workspace_bytes,
+                                               void* cuda_stream) {
+    if (!lambdas || !win_lengths || !n_ffts || !ys || !workspaces || !workspace_bytes) return DMEL_ERR_NULL_POINTER;
+    if (n_lambda <= 0 || n_lambda > DMEL_MAX_MULTI_LAMBDA) return DMEL_ERR_BAD_GEOMETRY;
+    if (n_mels > 0 && !banks) return DMEL_ERR_NULL_POINTER;
+    const float* means0 = nullptr;
+    for (int k = 0; k < n_lambda; ++k) {
+        // the per-clip means (models.py:38) do not depend on lambda: the first pass sums them, the others copy them
+        const int rc = forward_impl(x, batch, n_points, x_row_stride, lambdas[k], win_lengths[k], n_ffts[k], hop, n_mels,
+                                    n_mels > 0 ? banks[k] : nullptr, log_eps, flags, ys[k], nullptr, workspaces[k],
+                                    workspace_bytes[k], cuda_stream, means0);
+        if (rc) return rc;
+        if (k == 0 && !(flags & DMEL_FLAG_KEEP_MEAN)) means0 = ws_view(workspaces[0], batch, n_ffts[0]).means;
+    }
+    return DMEL_OK;
 }
 
 extern "C" DMEL_API int dmel_jvp_supported(int32_t n_fft) { const FftInfo fi = fft_info(n_fft); return (fi.ok && !fi.big) ? 1 : 0; }

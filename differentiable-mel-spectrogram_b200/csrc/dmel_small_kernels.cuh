@@ -116,7 +116,7 @@ dmel_segment_kernel(MelDev mel, int n_mels, int n_fft, int gt, SegView sv) {
 // grid = (B + 1) clusters of prep_segments(N) CTAs: cluster b < B -> mean of clip b; cluster B -> window + twiddles
 __global__ void __launch_bounds__(PREP_THREADS)
 dmel_prep_kernel(const void* __restrict__ x_any, long long x_stride, int B, int N, float lam_abs, int win_length,
-                 int n_fft, int flags, WsView ws, PlanDesc plan) {
+                 int n_fft, int flags, WsView ws, PlanDesc plan, const float* __restrict__ means_src) {
     const float* x = static_cast<const float*>(x_any);
     __shared__ double red[32];
     __shared__ double seg_total;
@@ -127,6 +127,10 @@ dmel_prep_kernel(const void* __restrict__ x_any, long long x_stride, int B, int 
     if (clip < B) {
         if (flags & DMEL_FLAG_KEEP_MEAN) {
             if (tid == 0 && seg == 0) ws.means[clip] = 0.f;
+            return;
+        }
+        if (means_src) {   // dmel_forward_multi_f32: the means of this batch already exist (they do not depend on lambda)
+            if (tid == 0 && seg == 0) ws.means[clip] = __ldg(means_src + clip);
             return;
         }
         // models.py:38  x[idx] - torch.mean(x[idx])

@@ -118,7 +118,7 @@ template <> struct InstNG<128>  { static constexpr int A = 8, B = 4; };
 template <> struct InstNG<256>  { static constexpr int A = 8, B = 4; };
 template <> struct InstNG<512>  { static constexpr int A = 8, B = 4; };
 template <> struct InstNG<1024> { static constexpr int A = 4, B = 2; };
-template <> struct InstNG<2048> { static constexpr int A = 2, B = 1; };
+template <> struct InstNG<2048> { static constexpr int A = 4, B = 1; };
 template <> struct InstNG<4096> { static constexpr int A = 1, B = 1; };
 
 #define DMEL_CAT_(a, b) a##b
