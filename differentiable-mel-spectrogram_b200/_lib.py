@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmel_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
-ABI_VERSION = 3
+ABI_VERSION = 4
 FLAG_NORMALIZE_WINDOW = 1
 FLAG_KEEP_MEAN = 2
 FLAG_TIME_MAJOR = 4
@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "dmel_workspace_y_sum_offset",
     "dmel_forward_f32",
     "dmel_forward_jvp_f32",
+    "dmel_forward_multi_f32",
     "dmel_jvp_supported",
     "dmel_x16_supported",
     "dmel_segment_table_bytes",
@@ -136,6 +137,14 @@ def _declare(lib: ctypes.CDLL) -> None:
     ]
     lib.dmel_forward_jvp_f32.restype = c.c_int
     lib.dmel_forward_jvp_f32.argtypes = lib.dmel_forward_f32.argtypes[:13] + [c.c_void_p] + lib.dmel_forward_f32.argtypes[13:]
+    lib.dmel_forward_multi_f32.restype = c.c_int
+    lib.dmel_forward_multi_f32.argtypes = [
+        c.c_void_p, c.c_int64, c.c_int64, c.c_int64,          # x, batch, n_points, stride
+        c.c_int32, c.POINTER(c.c_float), c.POINTER(c.c_int32), c.POINTER(c.c_int32),   # n_lambda, lambdas, wins, n_ffts
+        c.c_int32, c.c_int32, c.POINTER(c.POINTER(MelBankStruct)), c.c_float,          # hop, n_mels, banks, log_eps
+        c.c_int32, c.POINTER(c.c_void_p),                     # flags, ys
+        c.POINTER(c.c_void_p), c.POINTER(c.c_size_t), c.c_void_p,                      # workspaces, bytes, stream
+    ]
     lib.dmel_jvp_supported.restype = c.c_int
     lib.dmel_jvp_supported.argtypes = [c.c_int32]
     lib.dmel_x16_supported.restype = c.c_int

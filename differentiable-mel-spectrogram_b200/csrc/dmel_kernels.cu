@@ -238,7 +238,13 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
             if (f2.ok) { ng_pref = 2; sf_pref = (bwd && !need_dx) ? 4 : 8; }   // r02h sweep (profiles/)
             else { ng_pref = (bwd && need_dx) ? 4 : 2; sf_pref = (bwd && need_dx) ? 4 : 8; }
             break;
-        case 2048: ng_pref = 1; sf_pref = (f2.ok && !bwd && !jvp) ? 4 : 8; break;
+        case 2048:
+            // 128 threads per transform: one group per CTA leaves 8-12 warps per SM (shared memory bounds the CTAs), too few
+            // to cover the exchange latency; four groups share one copy of the tables (r02o, profiles/r02: backward
+            // -9 %, lambda-only backward -10 %, forward -3 %; the forward-mode forward keeps one group)
+            if (jvp) { ng_pref = 1; sf_pref = 8; }
+            else { ng_pref = 4; sf_pref = (bwd && need_dx) ? 4 : 8; }
+            break;
         case 4096: ng_pref = 1; sf_pref = 32; break;
         case 256: ng_pref = f2.ok ? 8 : 4; sf_pref = f2.ok ? 2 : 4; break;   // gen 2: half a warp per transform
         default: ng_pref = 4; sf_pref = 4; break;    // one warp per transform

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .op import dmel, workspace_energy
+from .op import dmel, dmel_multi, workspace_energy
 
 
 class _LambdaMirror:
@@ -121,6 +121,22 @@ class MelSpectrogramLayer(nn.Module):
                                 log_eps=self.log_eps, lambd_value=self._mirror.get(self.lambd), return_workspace=True,
                                 time_major=self.time_major, out_affine=self._affine_on(dev))
         return y
+
+    def forward_grid(self, x, lambdas):
+        """This front-end at several FIXED window widths over one batch (the reference's fixed-lambda grid,
+        search_spaces.py:22,29: one Ray trial per lambda, each re-reading the same clips): a list of outputs, entry k
+        bit-identical to what this layer returns with `lambd = lambdas[k]`.  No gradients (the grid is the
+        `trainable=False` case); the output affine map is not applied."""
+        dev = _resolve_device(self.device, self.lambd)
+        if dev.type != 'cuda':
+            raise _lib.DmelError(f"MelSpectrogramLayer lives on {dev}: this implementation is CUDA-only (sm_100a)")
+        if x.device != dev:
+            x = x.to(dev, non_blocking=True)
+        if x.shape[1] // self.hop_length + 1 != self.n_time:
+            raise RuntimeError(f"input has {x.shape[1]} points, layer was built for n_time={self.n_time}")
+        return dmel_multi(x, lambdas, hop_length=self.hop_length, optimized=self.optimized,
+                          normalize_window=self.normalize_window, n_mels=self.n_mels, sample_rate=self.sample_rate,
+                          f_min=self.f_min, f_max=self.f_max, log_eps=self.log_eps, time_major=self.time_major)
 
     @property
     def last_energy(self):

@@ -316,6 +316,66 @@ _plan_cache: dict = {}
 _affine_cache: dict = {}
 
 
+def dmel_multi(x: torch.Tensor, lambdas, *, hop_length: int, optimized: bool, normalize_window: bool = False,
+               n_mels: int = 0, sample_rate: int = 0, f_min: float = 0.0, f_max: Optional[float] = None,
+               log_eps: Optional[float] = None, remove_mean: bool = True, time_major: bool = False):
+    """One batch through several FIXED window widths in one call: the fixed-lambda grid of the reference's search
+    spaces (search_spaces.py:22,29 — `trainable=False` with lambda in {10, 35, 300 ms} * sample_rate / 6), where each
+    grid point is the same front-end applied to the same clips.  Returns a list with one (B, 1, rows, T) tensor per
+    lambda, each bit-identical to `dmel(x, lambda_k, ...)`; the per-clip means of models.py:38 are summed once and
+    shared, and x is read (and, for 16-bit input, widened) from the one device tensor.  No autograd: the grid is the
+    non-trainable case (for a trainable lambd use `dmel` / the layers)."""
+    import ctypes
+    if x.dim() != 2:
+        raise ValueError(f"expected x of shape (batch, n_points), got {tuple(x.shape)}")
+    _require_cuda(x, "x")
+    lams = [float(v) for v in (lambdas.detach().flatten().tolist() if isinstance(lambdas, torch.Tensor) else lambdas)]
+    if not lams:
+        raise ValueError("dmel_multi needs at least one lambda")
+    lib = _lib.load()
+    B, N = x.shape
+    geos = [resolve_geometry(B, N, hop_length, lam, optimized, n_mels) for lam in lams]
+    for geo, lam in zip(geos, lams):
+        if not lib.dmel_nfft_supported(geo.n_fft):
+            raise _lib.DmelError(f"n_fft={geo.n_fft} (lambd={lam}) has no kernel")
+        if time_major and not lib.dmel_jvp_supported(geo.n_fft):
+            raise _lib.DmelError(f"time_major output is implemented for n_fft 128..4096, got {geo.n_fft}")
+    flags = ((_lib.FLAG_NORMALIZE_WINDOW if normalize_window else 0) | (0 if remove_mean else _lib.FLAG_KEEP_MEAN)
+             | (_lib.FLAG_TIME_MAJOR if time_major else 0))
+    # 16-bit samples are widened in the kernels only if every entry's kernel family stages them
+    if x.dtype in (torch.int16, torch.float16) and all(lib.dmel_x16_supported(g.n_fft) for g in geos):
+        flags |= _lib.FLAG_X_I16 if x.dtype == torch.int16 else _lib.FLAG_X_F16
+    elif x.dtype != torch.float32:
+        x = x.to(torch.float32)
+    if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
+        x = x.contiguous()
+    if log_eps is not None and log_eps < 0:
+        raise ValueError("log_eps must be >= 0")
+    eps = -1.0 if log_eps is None else float(log_eps)
+    K = len(lams)
+    banks = None
+    bank_objs = []
+    if n_mels > 0:
+        fmax = f_max if f_max is not None else sample_rate // 2
+        bank_objs = [device_bank(g.n_freqs, f_min, fmax, n_mels, sample_rate, x.device) for g in geos]
+        banks = (ctypes.POINTER(_lib.MelBankStruct) * K)(*[ctypes.pointer(b.struct) for b in bank_objs])
+    ys, wss = [], []
+    for g in geos:
+        shape = (B, 1, g.n_frames, g.rows) if time_major else (B, 1, g.rows, g.n_frames)
+        ys.append(torch.empty(shape, dtype=torch.float32, device=x.device))
+        wss.append(torch.empty(int(lib.dmel_workspace_bytes(B, g.n_fft)), dtype=torch.uint8, device=x.device))
+    with _on_device(x.device):
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(lib.dmel_forward_multi_f32(
+            x.data_ptr(), B, N, x.stride(0), K, (ctypes.c_float * K)(*lams),
+            (ctypes.c_int32 * K)(*[g.win_length for g in geos]), (ctypes.c_int32 * K)(*[g.n_fft for g in geos]),
+            hop_length, n_mels, banks, eps, flags, (ctypes.c_void_p * K)(*[y.data_ptr() for y in ys]),
+            (ctypes.c_void_p * K)(*[w.data_ptr() for w in wss]), (ctypes.c_size_t * K)(*[w.numel() for w in wss]), st),
+            "dmel_forward_multi_f32")
+    del bank_objs
+    return ys
+
+
 def query_launch(batch: int, n_points: int, n_fft: int, hop: int, rows: int, bank_nnz: int = 0,
                  which: int = 0) -> dict:
     """What the launcher would pick: frames per CTA tile, FFT groups per CTA, dynamic shared memory, threads per

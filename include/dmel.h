@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DMEL_ABI_VERSION 3
+#define DMEL_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define DMEL_API __attribute__((visibility("default")))
@@ -154,6 +154,22 @@ DMEL_API int dmel_forward_f32(const void* x, int64_t batch, int64_t n_points, in
                      int32_t n_mels, const dmel_melbank* bank, float log_eps,
                      int32_t flags, float* y,
                      void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Several window widths over ONE batch in one call: the fixed-lambda grid of the reference's search spaces
+ * (search_spaces.py:22,29 — `trainable=False` x {10, 35, 300 ms}), where every grid point is the same front-end with a
+ * different lambda applied to the same clips.  Output k is what dmel_forward_f32 returns for lambdas[k] (bit-identical);
+ * what is shared is everything that does not depend on lambda: argument validation, the upload of x and the per-clip
+ * means of models.py:38, which are summed once (first entry) and copied for the others instead of re-reading x.
+ * Per entry k: lambdas[k], win_lengths[k], n_ffts[k], banks[k] (NULL array iff n_mels == 0), ys[k], and its own
+ * workspace (>= dmel_workspace_bytes(batch, n_ffts[k])), which a later dmel_backward_f32(prepared = 1) for that
+ * lambda may reuse.  Entries may mix transform lengths (and so the tiled, big-FFT and direct-DFT paths).             */
+#define DMEL_MAX_MULTI_LAMBDA 64
+DMEL_API int dmel_forward_multi_f32(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride,
+                                    int32_t n_lambda, const float* lambdas, const int32_t* win_lengths,
+                                    const int32_t* n_ffts, int32_t hop, int32_t n_mels,
+                                    const dmel_melbank* const* banks, float log_eps, int32_t flags,
+                                    float* const* ys, void* const* workspaces, const size_t* workspace_bytes,
+                                    void* cuda_stream);
 
 /* Forward-mode variant for the reference's training case (x is data, only `lambd` trains: models.py:19,
  * main.py:27).  Same arguments and the same y as dmel_forward_f32, plus dy_dlambda [batch,1,rows,T]:

@@ -664,3 +664,45 @@ def test_c_host_runs_the_abi_without_torch(cuda_device):
     for c in cases:
         out = subprocess.run([exe, "check", c], capture_output=True, text=True, timeout=120)
         assert out.returncode == 0 and "PASS" in out.stdout, (c, out.stdout, out.stderr)
+
+
+@pytest.mark.parametrize("sr,N,hop,M,windows_ms,dtype", [
+    (8000, 8000, 80, 64, (10, 35, 300), torch.float32),       # the reference's grid at 8 kHz: n_fft 128 / 512 / 4096
+    (16000, 16000, 160, 128, (10, 35, 300), torch.float32),   # 16 kHz: n_fft 256 / 1024 / 8192 (tiled + big-FFT paths)
+    (8000, 4000, 40, 0, (35, 35.5, 20), torch.float32),       # spectrogram mode, two entries sharing one n_fft
+    (8000, 8000, 80, 64, (35, 70), torch.int16),              # PCM clips, widened in the kernels
+])
+def test_fixed_lambda_grid_in_one_call(cuda_device, sr, N, hop, M, windows_ms, dtype):
+    """SURVEY.md §8(f)-4 / search_spaces.py:22,29 (trainable=False x lambda in {10, 35, 300 ms} * sr / 6): one
+    dmel_forward_multi_f32 call over the grid returns, per lambda, exactly what a separate forward returns (the per-clip
+    means are summed once and shared), and the first entry matches the oracle."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(21)
+    B = 3
+    xf = torch.randn(B, N, generator=g)
+    x = (xf * 3000.0).round().clamp(-32768, 32767).to(torch.int16) if dtype == torch.int16 else xf
+    lams = [sr * ms * 1e-3 / 6 for ms in windows_ms]
+    xd = x.to(dev)
+    ys = dm.dmel_multi(xd, lams, hop_length=hop, optimized=True, n_mels=M, sample_rate=sr, log_eps=EPS)
+    assert len(ys) == len(lams)
+    for lam, y in zip(lams, ys):
+        single = dm.dmel(xd, torch.tensor(float(lam), device=dev), hop_length=hop, optimized=True, n_mels=M,
+                         sample_rate=sr, log_eps=EPS)
+        assert y.shape == single.shape
+        assert torch.equal(y, single), f"lambda {lam}: grid output differs from the single call"
+    want = orc.port_forward(x.to(torch.float32), torch.tensor(float(lams[0])), hop=hop, optimized=True, norm=False,
+                            n_mels=M, sample_rate=sr)
+    check_y(ys[0].cpu().numpy(), torch.log(want + EPS).numpy(), False)
+
+
+def test_layer_forward_grid(cuda_device):
+    dev = cuda_device
+    sr, N, hop, M = 8000, 8000, 80, 64
+    x = torch.randn(2, N, generator=torch.Generator().manual_seed(3)).to(dev)
+    layer = dm.MelSpectrogramLayer(torch.tensor(sr * 0.035 / 6), n_mels=M, n_points=N, sample_rate=sr, hop_length=hop,
+                                   device=str(dev), optimized=True, log_eps=EPS).to(dev)
+    lams = [sr * 0.010 / 6, sr * 0.035 / 6]
+    ys = layer.forward_grid(x, lams)
+    with torch.no_grad():
+        assert torch.equal(ys[1], layer(x))
+    assert ys[0].shape == ys[1].shape == (2, 1, M, N // hop + 1)

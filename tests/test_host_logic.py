@@ -20,7 +20,7 @@ def test_library_loads_and_exports_header_symbols():
     assert declared == set(dm._lib.EXPORTED_SYMBOLS), declared ^ set(dm._lib.EXPORTED_SYMBOLS)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.dmel_abi_version() == 3
+    assert lib.dmel_abi_version() == 4
     assert lib.dmel_status_string(0) == b"ok"
     assert b"n_fft" in lib.dmel_status_string(-3)
 
