@@ -175,7 +175,7 @@ def test_launch_plans_fit_shared_memory():
         for which in (0, 1, 2):
             q = dm.query_launch(B, N, L, hop, r, 0 if spec else 2 * (L // 2 + 1), which)
             assert q["path"] == 0 and q["smem_bytes"] <= 227 * 1024 and q["tile_frames"] % 2 == 0, q
-            assert q["threads"] in (128, 256) and q["groups"] in (1, 2, 4, 8), q
+            assert q["threads"] in (128, 256, 512) and q["groups"] in (1, 2, 4, 8), q
     assert dm.query_launch(2, 100, 200, 5, 101, 0, 1)["path"] == 1           # non power of two -> direct DFT path
     for L, threads in ((8192, 256), (16384, 512)):                           # big-FFT path: one CTA per transform
         for which in (0, 1, 2):
