@@ -55,6 +55,7 @@
 #include "dmel_tiled2_kernels.cuh"  // themselves are instantiated in inst_tiled.cu
 #include "dmel_big_kernels.cuh"
 #include "dmel_dft_kernels.cuh"
+#include "dmel_dftmm_kernels.cuh"
 
 namespace dmel {
 
@@ -502,6 +503,45 @@ static int row_alignment_ok(const void* x, int64_t stride, int dtype) {
     return ((reinterpret_cast<uintptr_t>(x) & mask) == 0 && (stride & 3) == 0) ? 1 : 0;
 }
 
+// Short windows (even n_fft < 128), plain forward: DFT by matrix multiply on the tensor cores (dmel_dftmm_kernels.cuh)
+// instead of the O(L^2) CUDA-core DFT: 4.3x (n_fft 64, batch 512) to 5.9x (batch 4096) faster.  n_fft 128 itself stays
+// on the shared-memory FFT, which is 2x faster than the tensor-core kernel at every batch size measured
+// (profiles/r02/r02s_dftmm_vs_cuda_cores.log; the ncu capture next to it shows why: the thread-per-frame epilogue, not the
+// MMA, bounds it).  DMEL_NO_DFTMM=1 keeps the CUDA-core kernels, DMEL_DFTMM_128=1 also sends n_fft 128 to the tensor
+// cores (A/B measurements, tests).
+static bool dftmm_enabled() {
+    static const bool off = getenv("DMEL_NO_DFTMM") != nullptr && atoi(getenv("DMEL_NO_DFTMM")) != 0;
+    return !off;
+}
+static bool dftmm_takes_128() {
+    static const bool on = getenv("DMEL_DFTMM_128") != nullptr && atoi(getenv("DMEL_DFTMM_128")) != 0;
+    return on;
+}
+static bool dftmm_serves(int32_t n_fft, int32_t n_mels, const dmel_melbank* bank, int32_t flags, const float* dy) {
+    if (!dftmm_enabled() || dy != nullptr) return false;
+    if (n_fft < 4 || n_fft > mm::MAX_NFFT || (n_fft & 1)) return false;
+    if (n_fft == 128 && !dftmm_takes_128()) return false;
+    if (flags & (DMEL_FLAG_TIME_MAJOR | DMEL_FLAG_X_I16 | DMEL_FLAG_X_F16)) return false;
+    if (n_mels > 0 && bank->out_scale != nullptr) return false;
+    return true;
+}
+static int launch_dftmm_fwd(const float* x, float* y, int64_t B, int64_t N, int64_t stride, int32_t n_fft, int32_t hop,
+                            int32_t n_mels, float log_eps, const MelDev& mel, const WsView& ws, cudaStream_t st) {
+    static KernelCache kc;
+    int rc;
+    if ((rc = set_smem(mm::dmel_dftmm_fwd_kernel, size_t(mm::SMEM_BYTES), &kc))) return rc;
+    mm::MmGeom g{};
+    g.B = int(B); g.N = int(N); g.T = int(N / hop + 1); g.hop = hop; g.L = n_fft; g.M = n_mels;
+    g.x_stride = stride; g.log_eps = log_eps;
+    const int64_t tiles = (int64_t(g.B) * g.T + mm::ROWS - 1) / mm::ROWS;
+    int sms = NUM_SMS, dev = current_device(), v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+    const unsigned grid = unsigned(std::min<int64_t>(tiles, sms));
+    ProfScope prof(PROF_FWD, st);
+    mm::dmel_dftmm_fwd_kernel<<<grid, mm::THREADS, mm::SMEM_BYTES, st>>>(x, y, g, mel, ws.win, ws.means, ws.hdr);
+    return check_launch("dmel_dftmm_fwd_kernel");
+}
+
 static int forward_impl(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride, float lambda,
                         int32_t win_length, int32_t n_fft, int32_t hop, int32_t n_mels, const dmel_melbank* bank,
                         float log_eps, int32_t flags, float* y, float* dy, void* workspace, size_t workspace_bytes,
@@ -531,6 +571,8 @@ static int forward_impl(const void* x, int64_t batch, int64_t n_points, int64_t 
     g.row_aligned = row_alignment_ok(x, x_row_stride, x_dtype);
     g.time_major = (flags & DMEL_FLAG_TIME_MAJOR) ? 1 : 0;
     const float* xf = static_cast<const float*>(x);
+    if (dftmm_serves(n_fft, n_mels, bank, flags, dy))
+        return launch_dftmm_fwd(xf, y, batch, n_points, x_row_stride, n_fft, hop, n_mels, log_eps, mel, ws, st);
     if (lp.path == 1) {
         if ((rc = set_smem(dmel_dft_kernel<false, false>, lp.smem))) return rc;
         ProfScope prof(PROF_FWD, st);

@@ -706,3 +706,27 @@ def test_layer_forward_grid(cuda_device):
     with torch.no_grad():
         assert torch.equal(ys[1], layer(x))
     assert ys[0].shape == ys[1].shape == (2, 1, M, N // hop + 1)
+
+
+@pytest.mark.parametrize("n_fft,M,hop,log", [(64, 32, 40, True), (32, 16, 16, True), (64, 0, 20, False), (16, 0, 3, False),
+                                             (128, 64, 80, True)])
+def test_tensor_core_dft_forward(cuda_device, n_fft, M, hop, log):
+    """dmel_dftmm_kernels.cuh: even n_fft <= 128 run the forward as a 3xTF32 DFT-by-matrix-multiply on tcgen05 (n_fft 128
+    only with DMEL_DFTMM_128=1; by default it stays on the FFT and this case checks that path).  Same oracle, same
+    tolerances; several tiles of 128 frames, frames numbered across clips, a ragged last tile."""
+    dev = cuda_device
+    sr, N, B = 8000, 4000, 7
+    lam = 0.75 * n_fft / 6
+    assert orc.window_length(lam, N, True)[1] == n_fft
+    g = torch.Generator().manual_seed(n_fft + M)
+    x = torch.randn(B, N, generator=g) * 0.3 + 0.1
+    y = dm.dmel(x.to(dev), torch.tensor(float(lam), device=dev), hop_length=hop, optimized=True, n_mels=M, sample_rate=sr,
+                log_eps=EPS if log else None)
+    want = orc.port_forward(x, torch.tensor(float(lam)), hop=hop, optimized=True, norm=False, n_mels=M, sample_rate=sr)
+    if log:
+        want = torch.log(want + EPS)
+    check_y(y.cpu().numpy(), want.numpy(), not log)
+    # the fused energy by-product (train.py:58) comes out of this kernel family too
+    y2, energy = dm.dmel(x.to(dev), torch.tensor(float(lam), device=dev), hop_length=hop, optimized=True, n_mels=M,
+                         sample_rate=sr, log_eps=EPS if log else None, return_energy=True)
+    assert abs(float(energy) - float(y2.double().sum())) <= 1e-5 * float(y2.double().abs().sum())
