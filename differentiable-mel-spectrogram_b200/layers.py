@@ -103,6 +103,8 @@ class MelSpectrogramLayer(nn.Module):
         self.set_output_affine(scale, shift)
 
     def forward(self, x):
+        # CUDA graphs: lambd goes to the kernels by value (its magnitude picks n_fft and the launch plan on the host), so a
+        # captured step keeps the lambd of capture time — re-capture after every optimiser step that changes it
         dev = _resolve_device(self.device, self.lambd)
         if dev.type != 'cuda':
             raise _lib.DmelError(

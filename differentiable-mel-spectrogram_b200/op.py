@@ -55,9 +55,9 @@ class Geometry:
 
 
 def resolve_geometry(batch: int, n_points: int, hop: int, lambd_value: float, optimized: bool,
-                     n_mels: int = 0) -> Geometry:
+                     n_mels: int = 0, n_stds: int = 6) -> Geometry:
     if optimized:
-        win = window_length_from_lambda(lambd_value)
+        win = window_length_from_lambda(lambd_value, n_stds)
         n_fft = win
     else:
         win = int(n_points)
@@ -220,8 +220,10 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
          normalize_window: bool = False, n_mels: int = 0, sample_rate: int = 0, f_min: float = 0.0,
          f_max: Optional[float] = None, log_eps: Optional[float] = None, remove_mean: bool = True,
          lambd_value: Optional[float] = None, return_energy: bool = False, time_major: bool = False,
-         out_affine: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, return_workspace: bool = False):
-    """Functional form of both layers.
+         out_affine: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, return_workspace: bool = False,
+         n_stds: int = 6):
+    """Functional form of both layers.  `n_stds` is time_frequency.py:32's window support in standard deviations
+    (optimized mode: window_length = next_power_of_2(int(n_stds * |lambd|)); the layers use the reference's 6).
 
     x: (B, N) CUDA tensor (fp32; fp64/fp16 inputs are cast to fp32 — the reference's fp64
     synthetic dataset ends in an fp32 output buffer anyway, models.py:189).  Returns
@@ -263,10 +265,10 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
         raise ValueError("log_eps must be >= 0")
     # everything below depends only on these scalars: resolve once, reuse while they repeat (training loops)
     key = (B, N, hop_length, lam_value, optimized, normalize_window, n_mels, sample_rate, f_min, f_max, log_eps, remove_mean,
-           time_major, x.device.index, x16_flag)
+           time_major, x.device.index, x16_flag, n_stds)
     plan = _plan_cache.get(key)
     if plan is None:
-        geo = resolve_geometry(B, N, hop_length, lam_value, optimized, n_mels)
+        geo = resolve_geometry(B, N, hop_length, lam_value, optimized, n_mels, n_stds)
         lib = _lib.load()
         if not lib.dmel_nfft_supported(geo.n_fft):
             raise _lib.DmelError(f"n_fft={geo.n_fft} (lambd={lam_value}) has no kernel")

@@ -24,8 +24,6 @@ def differentiable_gaussian_window(lambd, window_length, device='cpu', norm=True
 def differentiable_spectrogram(x, lambd, optimized=False, device='cpu', hop_length=1, return_window=False,
                                norm=False, n_stds=6):
     """|STFT|^2 of one signal x (n_points,) with the Gaussian window of width lambd -> (F, T)."""
-    if n_stds != 6:
-        raise NotImplementedError("the kernels implement the reference's only setting n_stds=6")
     if x.dim() != 1:
         raise ValueError("x must be one signal of shape (n_points,)")
     lam = lambd if torch.is_tensor(lambd) else torch.tensor(float(lambd))
@@ -34,7 +32,7 @@ def differentiable_spectrogram(x, lambd, optimized=False, device='cpu', hop_leng
     # depends on lambd^2, so passing it through the op's |lambd| changes nothing but the sign
     # convention of d/dlambd for negative values, which abs() restores.
     s = dmel(x.unsqueeze(0), lam, hop_length=hop_length, optimized=optimized, normalize_window=norm,
-             n_mels=0, remove_mean=False)[0, 0]
+             n_mels=0, remove_mean=False, n_stds=n_stds)[0, 0]
     if not return_window:
         return s
     win_len = window_length_from_lambda(float(lam.detach()), n_stds) if optimized else x.shape[0]

@@ -730,3 +730,22 @@ def test_tensor_core_dft_forward(cuda_device, n_fft, M, hop, log):
     y2, energy = dm.dmel(x.to(dev), torch.tensor(float(lam), device=dev), hop_length=hop, optimized=True, n_mels=M,
                          sample_rate=sr, log_eps=EPS if log else None, return_energy=True)
     assert abs(float(energy) - float(y2.double().sum())) <= 1e-5 * float(y2.double().abs().sum())
+
+
+@pytest.mark.parametrize("n_stds", [4, 8])
+def test_window_support_in_standard_deviations(cuda_device, n_stds):
+    """time_frequency.py:32,39: differentiable_spectrogram(..., n_stds) sizes the optimized window as
+    next_power_of_2(int(n_stds * lambd)); the window formula itself does not change.  Against the reference's own
+    formula evaluated with torch.stft on the CPU."""
+    dev = cuda_device
+    lam, N, hop = 20.0, 2000, 16
+    x = torch.randn(N, generator=torch.Generator().manual_seed(n_stds))
+    got, win = dm.differentiable_spectrogram(x.to(dev), torch.tensor(lam, device=dev), optimized=True, hop_length=hop,
+                                             return_window=True, n_stds=n_stds)
+    L = orc.next_power_of_2(np.float32(lam) * np.float32(n_stds))
+    assert win.shape[0] == L
+    m = torch.arange(0, L).float()
+    w = torch.exp(-0.5 * torch.pow((m - L / 2) / (lam + 1e-15), 2))
+    want = torch.stft(x, n_fft=L, hop_length=hop, win_length=L, window=w, return_complex=True, pad_mode='constant').abs() ** 2
+    np.testing.assert_allclose(win.cpu().numpy(), w.numpy(), rtol=1e-6, atol=1e-7)
+    check_y(got.cpu().numpy(), want.numpy(), True)
