@@ -504,10 +504,10 @@ static int row_alignment_ok(const void* x, int64_t stride, int dtype) {
 }
 
 // Short windows (even n_fft < 128), plain forward: DFT by matrix multiply on the tensor cores (dmel_dftmm_kernels.cuh)
-// instead of the O(L^2) CUDA-core DFT: 4.3x (n_fft 64, batch 512) to 5.9x (batch 4096) faster.  n_fft 128 itself stays
-// on the shared-memory FFT, which is 2x faster than the tensor-core kernel at every batch size measured
-// (profiles/r02/r02s_dftmm_vs_cuda_cores.log; the ncu capture next to it shows why: the thread-per-frame epilogue, not the
-// MMA, bounds it).  DMEL_NO_DFTMM=1 keeps the CUDA-core kernels, DMEL_DFTMM_128=1 also sends n_fft 128 to the tensor
+// instead of the O(L^2) CUDA-core DFT: 5.6x (n_fft 64, batch 512) to 6.7x (batch 4096) faster.  n_fft 128 itself stays
+// on the shared-memory FFT, which is 1.5x faster than the tensor-core kernel at every batch size measured
+// (profiles/r02/r02z_dftmm_vs_cuda_cores.log; the subtractive builds next to it show why: the operand builders' loads and
+// the single-buffered build -> MMA latency chain, not the MMAs, bound it).  DMEL_NO_DFTMM=1 keeps the CUDA-core kernels, DMEL_DFTMM_128=1 also sends n_fft 128 to the tensor
 // cores (A/B measurements, tests).
 static bool dftmm_enabled() {
     static const bool off = getenv("DMEL_NO_DFTMM") != nullptr && atoi(getenv("DMEL_NO_DFTMM")) != 0;
@@ -523,6 +523,8 @@ static bool dftmm_serves(int32_t n_fft, int32_t n_mels, const dmel_melbank* bank
     if (n_fft == 128 && !dftmm_takes_128()) return false;
     if (flags & (DMEL_FLAG_TIME_MAJOR | DMEL_FLAG_X_I16 | DMEL_FLAG_X_F16)) return false;
     if (n_mels > 0 && bank->out_scale != nullptr) return false;
+    // the epilogue's chunk table (shared memory) is sized for this many mels / 4-tap chunks
+    if (n_mels > mm::MAX_MELS || (n_mels > 0 && bank->mel_nnz / 4 + n_mels > mm::MAX_CHUNKS)) return false;
     return true;
 }
 static int launch_dftmm_fwd(const float* x, float* y, int64_t B, int64_t N, int64_t stride, int32_t n_fft, int32_t hop,
