@@ -113,6 +113,7 @@ struct Geom {
     int time_major;              // y / dL/dy / dy are (B,1,T,rows) instead of (B,1,rows,T)
     int x_dtype;                 // DMEL_X_F32 / DMEL_X_I16 / DMEL_X_F16 (16-bit inputs: second-generation tiled kernels only;
                                  // row_aligned then means 8-byte alignment of x and of the row stride)
+    int dx_vec4;                 // backward: dx is 16-byte aligned and N a multiple of 4: tiles whose first sample is 4-aligned merge dx four samples at a time
 };
 
 struct MelDev {

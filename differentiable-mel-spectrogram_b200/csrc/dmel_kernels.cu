@@ -724,6 +724,7 @@ static int backward_impl(const void* x, int64_t batch, int64_t n_points, int64_t
     g.x_dtype = x_dtype;
     g.row_aligned = row_alignment_ok(x, x_row_stride, x_dtype);
     g.time_major = (flags & DMEL_FLAG_TIME_MAJOR) ? 1 : 0;
+    g.dx_vec4 = (grad_x != nullptr && (reinterpret_cast<uintptr_t>(grad_x) & 15) == 0 && (n_points & 3) == 0) ? 1 : 0;
     if (g.time_major && lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;
     const MelDev mel = mel_dev(bank);
 #ifdef DMEL_FAST_BUILD

@@ -724,6 +724,43 @@ dmel2_bwd_kernel(const void* __restrict__ x, const float* __restrict__ y, const 
             const float* priv0 = smem_f + lay.grp + round_up4(2 * F::BUF);
             const int gstep = sfe * g.hop;
             float part = 0.f;
+            if (g.dx_vec4 && (((p0 | gstep) & 3) == 0)) {
+                // dx rows are 16-byte aligned and this tile's first sample and the groups' offsets are multiples of 4: the merge
+                // moves 16 bytes per step (LDS.128 per group, one STG.128 or one vector reduction) instead of four scalar round
+                // trips.  A sub-span is zero-padded to a multiple of 4, so a quad may run past its end; only the quads that
+                // straddle the store / reduce boundaries take the per-sample path.
+                const unsigned ss4 = unsigned(round_up4(g.sub_span));
+                for (int i = 4 * tid; i < span_used; i += 4 * NT) {
+                    const int p = p0 + i;
+                    if (p >= 0 && p < g.N) {
+                        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int gi = 0; gi < NG; ++gi) {
+                            const int o = i - gi * gstep;
+                            if (unsigned(o) < ss4) {
+                                const float4 v = *reinterpret_cast<const float4*>(priv0 + gi * lay.grp_stride + o);
+                                val.x += v.x; val.y += v.y; val.z += v.z; val.w += v.w;
+                            }
+                        }
+                        val.x *= 2.f; val.y *= 2.f; val.z *= 2.f; val.w *= 2.f;
+                        part += (val.x + val.y) + (val.z + val.w);
+                        if (p >= excl_lo && p + 3 < excl_hi) {
+                            *reinterpret_cast<float4*>(dxb + p) = val;
+                        } else if (p + 3 < excl_lo || p >= excl_hi) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dxb + p), "f"(val.x), "f"(val.y),
+                                         "f"(val.z), "f"(val.w)
+                                         : "memory");
+                        } else {
+                            const float v4[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (p + j >= excl_lo && p + j < excl_hi) dxb[p + j] = v4[j];
+                                else atomicAdd(dxb + p + j, v4[j]);
+                            }
+                        }
+                    }
+                }
+            } else
             for (int i = tid; i < span_used; i += NT) {
                 const int p = p0 + i;
                 if (p >= 0 && p < g.N) {

@@ -5,7 +5,8 @@ sample_rate)` on the CPU for every sample of every batch (models.py:42-51) and m
 dense (F, M) matrix (models.py:53).  torchaudio is a third-party dependency of the reference
 (pinned torchaudio==0.13.1 in requirements.txt, not vendored), so its published algorithm is
 restated here — HTK mel scale, triangular filters, norm=None — with the same fp32 operation
-order, and tests/test_melbank.py pins it bit-for-bit against the torchaudio in this image.
+order, and tests/test_host_logic.py (test_melbank_bit_identical_to_torchaudio_and_pack_roundtrip) pins it bit-for-bit against
+the torchaudio in this image.
 
 The kernels never see the dense matrix: every frequency bin has at most two non-zero mel
 weights, so the bank is shipped as two CSR-like forms (see include/dmel.h, dmel_melbank).
