@@ -31,3 +31,19 @@ for ci, (N, sr, hop, M, lam, opt) in enumerate(cases):
     y2.backward(torch.ones_like(y2))
     torch.cuda.synchronize()
     print("case", ci, tuple(y.shape), "ok", flush=True)
+# round 2: 16-bit samples widened in the kernels, the fixed-lambda grid in one call (shared means), the tensor-core
+# DFT with a mel bank and in spectrogram mode over several tiles, forward-mode forward at n_fft 2048 (one group per CTA)
+xi = (torch.randn(3, 1600, generator=g) * 3000).to(torch.int16).to(dev)
+ll = torch.tensor(46.667, device=dev, requires_grad=True)
+y = dm.dmel(xi, ll, hop_length=80, optimized=True, n_mels=32, sample_rate=8000, log_eps=1e-10)
+y.backward(torch.randn(y.shape, generator=g).to(dev))
+ys = dm.dmel_multi(torch.randn(3, 1600, generator=g).to(dev), [8.0, 13.33, 46.667, 400.0], hop_length=80, optimized=True, n_mels=32,
+                   sample_rate=8000, log_eps=1e-10)
+ym = dm.dmel(torch.randn(5, 4000, generator=g).to(dev), torch.tensor(8.0, device=dev), hop_length=20, optimized=True, n_mels=24,
+             sample_rate=8000, log_eps=1e-10)
+ysp = dm.dmel(torch.randn(5, 4000, generator=g).to(dev), torch.tensor(4.0, device=dev), hop_length=10, optimized=True, n_mels=0)
+ll2 = torch.tensor(257.25, device=dev, requires_grad=True)
+yj = dm.dmel(torch.randn(2, 6000, generator=g).to(dev), ll2, hop_length=441, optimized=True, n_mels=32, sample_rate=44100, log_eps=1e-10)
+yj.backward(torch.randn(yj.shape, generator=g).to(dev))
+torch.cuda.synchronize()
+print("round-2 cases ok", flush=True)
