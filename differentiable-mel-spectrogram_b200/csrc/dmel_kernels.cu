@@ -727,10 +727,6 @@ static int backward_impl(const void* x, int64_t batch, int64_t n_points, int64_t
     g.dx_vec4 = (grad_x != nullptr && (reinterpret_cast<uintptr_t>(grad_x) & 15) == 0 && (n_points & 3) == 0) ? 1 : 0;
     if (g.time_major && lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;
     const MelDev mel = mel_dev(bank);
-#ifdef DMEL_FAST_BUILD
-    if (lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;
-    if (false) {
-#else
     if (lp.path == 1) {
         const unsigned grid = unsigned(int64_t(g.B) * g.T);
         ProfScope prof(PROF_BWD, st);
@@ -748,7 +744,6 @@ static int backward_impl(const void* x, int64_t batch, int64_t n_points, int64_t
         rc = n_fft == 8192 ? launch_big_bwd<8192>(xf, y, grad_y, grad_x, g, mel, spec, ws, lp, st)
                            : launch_big_bwd<16384>(xf, y, grad_y, grad_x, g, mel, spec, ws, lp, st);
         if (rc) return rc;
-#endif
     } else if (gen2) {
         switch (n_fft) {
 #define DMEL_CASE(LL) case LL: rc = launch_tiled2_bwd_##LL(lp.NG, x, y, grad_y, grad_x, g, mel, spec, ws, lp, st); break;
