@@ -93,7 +93,9 @@ static inline int current_device() {
 
 template <typename K>
 static int set_smem(K kernel, size_t smem, KernelCache* kc = nullptr) {
-    if (smem > 48 * 1024) {
+    // the 48 KB a kernel gets without opting in covers dynamic AND static shared memory (the tiled kernels keep a few
+    // hundred bytes of static tables): opt in from a margin below it
+    if (smem > 47 * 1024) {
         const int dev = current_device();
         if (kc && dev < MAX_DEVICES && kc->smem_ok[dev].load(std::memory_order_relaxed) >= smem) return DMEL_OK;
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));

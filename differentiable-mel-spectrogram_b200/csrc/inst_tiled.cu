@@ -71,7 +71,14 @@ static int launch_fwd2_t(const void* x, float* y, float* dy, const Geom& g, cons
     const unsigned grid = persistent_grid(v2::dmel2_fwd_kernel<L, NG, SPEC, JVP>, lp, int64_t(g.B) * g.tiles_per_clip, &kc);
     ProfScope prof(PROF_FWD, st);
     v2::dmel2_fwd_kernel<L, NG, SPEC, JVP><<<grid, lp.threads, lp.smem, st>>>(x, y, dy, g, mel, ws.win, ws.tw, ws.means, ws.hdr);
-    return check_launch("dmel2_fwd_kernel");
+    rc = check_launch("dmel2_fwd_kernel");
+    if (rc) {
+        cudaFuncAttributes fa{};
+        cudaFuncGetAttributes(&fa, v2::dmel2_fwd_kernel<L, NG, SPEC, JVP>);
+        fprintf(stderr, "[dmel] dmel2_fwd_kernel<%d,%d,%d,%d>: grid %u threads %d dynamic smem %zu (max dynamic %d, static %zu, regs %d)\n", L, NG,
+                int(SPEC), int(JVP), grid, lp.threads, lp.smem, fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes, fa.numRegs);
+    }
+    return rc;
 }
 
 template <int L, int NG, bool SPEC, bool NEED_DX>

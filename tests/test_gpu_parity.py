@@ -749,3 +749,18 @@ def test_window_support_in_standard_deviations(cuda_device, n_stds):
     want = torch.stft(x, n_fft=L, hop_length=hop, win_length=L, window=w, return_complex=True, pad_mode='constant').abs() ** 2
     np.testing.assert_allclose(win.cpu().numpy(), w.numpy(), rtol=1e-6, atol=1e-7)
     check_y(got.cpu().numpy(), want.numpy(), True)
+
+
+def test_dynamic_shared_memory_right_at_the_opt_in_threshold(cuda_device):
+    """The forward-mode kernel at n_fft 1024, 64 mels, hop 80 asks for exactly 48 KB of dynamic shared memory on top of its
+    64 bytes of static tables: it must opt in (the launch used to fail with 'invalid argument' — found by the n_fft sweep)."""
+    dev = cuda_device
+    x = torch.randn(4, 8000, generator=torch.Generator().manual_seed(1)).to(dev)
+    ll = torch.tensor(128.0, device=dev, requires_grad=True)
+    y = dm.dmel(x, ll, hop_length=80, optimized=True, n_mels=64, sample_rate=8000, log_eps=EPS)
+    G = torch.randn(y.shape, generator=torch.Generator().manual_seed(2)).to(dev)
+    (y * G).sum().backward()
+    want = orc.port_forward_backward(x.cpu(), 128.0, G.cpu(), use_log=True, batched=True, hop=80, optimized=True, n_mels=64,
+                                     sample_rate=8000)
+    check_y(y.detach().cpu().numpy(), want[0], False)
+    assert abs(float(ll.grad) - want[2]) <= G_RTOL * abs(want[2])
