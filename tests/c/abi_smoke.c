@@ -40,6 +40,26 @@ int main(void) {
     CHECK(dmel_forward_f32(&fake, 1, 100, 100, 10.f, 64, 64, 10, 4, &bank, -1.f, 0, &fake, &fake, 1 << 20, NULL)
           == DMEL_ERR_BAD_MELBANK);
 
+    /* the fixed-lambda grid entry point validates its arrays before any device work, then every entry like a forward */
+    {
+        const float lams[2] = {13.33f, 46.667f};
+        const int32_t wins[2] = {128, 512}, nffts[2] = {128, 512};
+        float* ys[2] = {&fake, &fake};
+        void* wss[2] = {&fake, &fake};
+        const size_t small[2] = {16, 16}, big[2] = {1 << 20, 1 << 20};
+        CHECK(dmel_forward_multi_f32(&fake, 1, 100, 100, 2, NULL, wins, nffts, 10, 0, NULL, -1.f, 0, ys, wss, big, NULL)
+              == DMEL_ERR_NULL_POINTER);
+        CHECK(dmel_forward_multi_f32(&fake, 1, 100, 100, 0, lams, wins, nffts, 10, 0, NULL, -1.f, 0, ys, wss, big, NULL)
+              == DMEL_ERR_BAD_GEOMETRY);
+        CHECK(dmel_forward_multi_f32(&fake, 1, 100, 100, DMEL_MAX_MULTI_LAMBDA + 1, lams, wins, nffts, 10, 0, NULL, -1.f, 0, ys,
+                                     wss, big, NULL) == DMEL_ERR_BAD_GEOMETRY);
+        CHECK(dmel_forward_multi_f32(&fake, 1, 100, 100, 2, lams, wins, nffts, 10, 0, NULL, -1.f, 0, ys, wss, small, NULL)
+              == DMEL_ERR_WORKSPACE_TOO_SMALL);
+        CHECK(dmel_forward_multi_f32(&fake, 1, 100, 100, 2, lams, wins, nffts, 10, 4, NULL, -1.f, 0, ys, wss, big, NULL)
+              == DMEL_ERR_NULL_POINTER);
+    }
+    CHECK(dmel_x16_supported(1024) == 1 && dmel_x16_supported(128) == 0 && dmel_jvp_supported(2048) == 1);
+
     int32_t tile = 0, groups = 0, smem = 0, threads = 0, path = -1;
     CHECK(dmel_query_launch(256, 8000, 512, 80, 64, 700, 0, &tile, &groups, &smem, &threads, &path) == DMEL_OK);
     CHECK(tile > 0 && groups > 0 && threads == groups * 32 && smem > 0 && smem <= 227 * 1024 && path == 0);
