@@ -2,6 +2,8 @@
 //   -DDMEL_INST_GEN=1|2  -DDMEL_INST_L=<n_fft>  -DDMEL_INST_DIR=0 (forward) | 1 (backward)
 // so that the heavy instantiations build in parallel (see Makefile).  The group counts per transform length must
 // match fft_info() / fft2_info() in dmel_kernels.cu.
+#include <stdlib.h>
+
 #include "dmel_host.cuh"
 #include "fft_device.cuh"
 #if DMEL_INST_GEN == 1
@@ -86,11 +88,15 @@ static int launch_bwd2_t(const void* x, const float* y, const float* gy, float* 
                          const WsView& ws, const LaunchPlan& lp, cudaStream_t st) {
     static KernelCache kc;     // one per instantiation
     int rc;
-    if ((rc = set_smem(v2::dmel2_bwd_kernel<L, NG, SPEC, NEED_DX>, lp.smem, &kc))) return rc;
-    const unsigned grid = persistent_grid(v2::dmel2_bwd_kernel<L, NG, SPEC, NEED_DX>, lp, int64_t(g.B) * g.tiles_per_clip, &kc);
+    // DMEL_EXP_PAD_SMEM: occupancy experiments — pad the request so that fewer CTAs fit per SM
+    static const size_t pad = getenv("DMEL_EXP_PAD_SMEM") ? size_t(atol(getenv("DMEL_EXP_PAD_SMEM"))) : 0;
+    LaunchPlan lpp = lp;
+    lpp.smem += pad;
+    if ((rc = set_smem(v2::dmel2_bwd_kernel<L, NG, SPEC, NEED_DX>, lpp.smem, &kc))) return rc;
+    const unsigned grid = persistent_grid(v2::dmel2_bwd_kernel<L, NG, SPEC, NEED_DX>, lpp, int64_t(g.B) * g.tiles_per_clip, &kc);
     ProfScope prof(PROF_BWD, st);
     v2::dmel2_bwd_kernel<L, NG, SPEC, NEED_DX>
-        <<<grid, lp.threads, lp.smem, st>>>(x, y, gy, dx, g, mel, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
+        <<<grid, lp.threads, lpp.smem, st>>>(x, y, gy, dx, g, mel, ws.win, ws.tw, ws.means, ws.hdr, ws.clipsum);
     return check_launch("dmel2_bwd_kernel");
 }
 
