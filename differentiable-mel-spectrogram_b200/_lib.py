@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "dmel_forward_jvp_f32",
     "dmel_forward_multi_f32",
     "dmel_jvp_supported",
+    "dmel_time_major_supported",
     "dmel_x16_supported",
     "dmel_segment_table_bytes",
     "dmel_build_segment_tables",
@@ -147,6 +148,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     ]
     lib.dmel_jvp_supported.restype = c.c_int
     lib.dmel_jvp_supported.argtypes = [c.c_int32]
+    lib.dmel_time_major_supported.restype = c.c_int
+    lib.dmel_time_major_supported.argtypes = [c.c_int32, c.c_int32]
     lib.dmel_x16_supported.restype = c.c_int
     lib.dmel_x16_supported.argtypes = [c.c_int32]
     lib.dmel_segment_table_bytes.restype = c.c_size_t

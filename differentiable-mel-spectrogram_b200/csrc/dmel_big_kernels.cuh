@@ -114,17 +114,25 @@ dmel_big_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, Geom g, 
     }
     if (!SPEC) {
         __syncthreads();
-        float* yb = y + (long long)b * g.M * g.T + t0;
-        const int tt_shift = ilog2(g.TT);
-        for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
-            const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
-            if (tt < nfr) {
-                float val = tile[m * TS + tt];
-                if (do_log) val = __logf(val + g.log_eps);
-                if (mel.out_scale) val = affine_out(mel, m, val);
-                yb[(long long)m * g.T + tt] = val;
-                ysum += val;
+        auto emit = [&](int m, int tt, long long off) {
+            float val = tile[m * TS + tt];
+            if (do_log) val = __logf(val + g.log_eps);
+            if (mel.out_scale) val = affine_out(mel, m, val);
+            y[off] = val;
+            ysum += val;
+        };
+        if (!g.time_major) {
+            const long long base = (long long)b * g.M * g.T + t0;
+            const int tt_shift = ilog2(g.TT);
+            for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
+                const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
+                if (tt < nfr) emit(m, tt, base + (long long)m * g.T + tt);
             }
+        } else {
+            // (B,1,T,M): what MelPANNsNet transposes to (models.py:162); consecutive lanes write consecutive mel bins
+            const long long base = ((long long)b * g.T + t0) * g.M;
+            for (int tt = tid >> 5; tt < nfr; tt += NT / 32)
+                for (int m = tid & 31; m < g.M; m += 32) emit(m, tt, base + (long long)tt * g.M + m);
         }
     }
     const double ytot = block_sum(double(ysum), reinterpret_cast<double*>(smem_f + lay.red));
@@ -166,17 +174,25 @@ dmel_big_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, co
     if (NEED_DX)
         for (int i = tid; i < g.span; i += NT) priv[i] = 0.f;
     if (!SPEC) {
-        const int tt_shift = ilog2(g.TT);
-        for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
-            const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
+        auto stage = [&](int m, int tt, long long off) {
             float val = 0.f;
             if (tt < nfr) {
-                const long long off = ybase + (long long)m * g.T + tt;
                 val = __ldg(gy + off);
                 if (mel.out_scale) val *= affine_grad_factor(mel, m, do_log ? __ldg(y + off) : 0.f, do_log);
                 else if (do_log) val *= __expf(-__ldg(y + off));
             }
             gt[m * TS + tt] = val;
+        };
+        if (!g.time_major) {
+            const int tt_shift = ilog2(g.TT);
+            for (int idx = tid; idx < (g.M << tt_shift); idx += NT) {
+                const int m = idx >> tt_shift, tt = idx & (g.TT - 1);
+                stage(m, tt, ybase + (long long)m * g.T + tt);
+            }
+        } else {
+            const long long base = ((long long)b * g.T + t0) * g.M;
+            for (int tt = tid >> 5; tt < g.TT; tt += NT / 32)
+                for (int m = tid & 31; m < g.M; m += 32) stage(m, tt, base + (long long)tt * g.M + m);
         }
     }
     __syncthreads();

@@ -559,7 +559,8 @@ static int forward_impl(const void* x, int64_t batch, int64_t n_points, int64_t 
                           false, &lp, dy != nullptr, !spec && bank->seg_tables != nullptr)))
         return rc;
     if (dy && lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;   // the JVP forward exists for the tiled FFT path only
-    if ((flags & DMEL_FLAG_TIME_MAJOR) && lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;   // likewise the (B,1,T,M) layout
+    // the (B,1,T,M) layout: tiled FFT kernels, and the big-FFT path in mel mode
+    if ((flags & DMEL_FLAG_TIME_MAJOR) && !(lp.path == 0 || (lp.path == 2 && !spec))) return DMEL_ERR_UNSUPPORTED_NFFT;
     if (int64_t(batch) * lp.tiles_per_clip > INT32_MAX) return DMEL_ERR_BAD_GEOMETRY;
     int x_dtype = DMEL_X_F32;
     if ((rc = x_dtype_of(flags, lp, &x_dtype))) return rc;
@@ -638,6 +639,11 @@ extern "C" DMEL_API int dmel_forward_multi_f32(const void* x, int64_t batch, int
 }
 
 extern "C" DMEL_API int dmel_jvp_supported(int32_t n_fft) { const FftInfo fi = fft_info(n_fft); return (fi.ok && !fi.big) ? 1 : 0; }
+
+extern "C" DMEL_API int dmel_time_major_supported(int32_t n_fft, int32_t n_mels) {
+    const FftInfo fi = fft_info(n_fft);
+    return (fi.ok && (!fi.big || n_mels > 0)) ? 1 : 0;
+}
 
 extern "C" DMEL_API int dmel_x16_supported(int32_t n_fft) { return fft2_info(n_fft).ok ? 1 : 0; }
 
@@ -725,7 +731,7 @@ static int backward_impl(const void* x, int64_t batch, int64_t n_points, int64_t
     g.row_aligned = row_alignment_ok(x, x_row_stride, x_dtype);
     g.time_major = (flags & DMEL_FLAG_TIME_MAJOR) ? 1 : 0;
     g.dx_vec4 = (grad_x != nullptr && (reinterpret_cast<uintptr_t>(grad_x) & 15) == 0 && (n_points & 3) == 0) ? 1 : 0;
-    if (g.time_major && lp.path != 0) return DMEL_ERR_UNSUPPORTED_NFFT;
+    if (g.time_major && !(lp.path == 0 || (lp.path == 2 && !spec))) return DMEL_ERR_UNSUPPORTED_NFFT;
     const MelDev mel = mel_dev(bank);
     if (lp.path == 1) {
         const unsigned grid = unsigned(int64_t(g.B) * g.T);

@@ -280,8 +280,9 @@ def dmel(x: torch.Tensor, lambd: torch.Tensor, *, hop_length: int, optimized: bo
                  | (_lib.FLAG_TIME_MAJOR if time_major else 0))
         if x16_flag and lib.dmel_x16_supported(geo.n_fft):
             flags |= x16_flag
-        if time_major and not lib.dmel_jvp_supported(geo.n_fft):
-            raise _lib.DmelError(f"time_major output is implemented for n_fft 128..4096, got {geo.n_fft}")
+        if time_major and not lib.dmel_time_major_supported(geo.n_fft, n_mels):
+            raise _lib.DmelError(f"time_major output is implemented for n_fft 128..4096 (and 8192 / 16384 with a mel bank), "
+                                 f"got n_fft={geo.n_fft}, n_mels={n_mels}")
         eps = -1.0 if log_eps is None else float(log_eps)
         plan = (geo, bank, eps, flags, int(lib.dmel_workspace_bytes(geo.batch, geo.n_fft)))
         if len(_plan_cache) > 64:
@@ -340,8 +341,9 @@ def dmel_multi(x: torch.Tensor, lambdas, *, hop_length: int, optimized: bool, no
     for geo, lam in zip(geos, lams):
         if not lib.dmel_nfft_supported(geo.n_fft):
             raise _lib.DmelError(f"n_fft={geo.n_fft} (lambd={lam}) has no kernel")
-        if time_major and not lib.dmel_jvp_supported(geo.n_fft):
-            raise _lib.DmelError(f"time_major output is implemented for n_fft 128..4096, got {geo.n_fft}")
+        if time_major and not lib.dmel_time_major_supported(geo.n_fft, n_mels):
+            raise _lib.DmelError(f"time_major output is implemented for n_fft 128..4096 (and 8192 / 16384 with a mel bank), "
+                                 f"got n_fft={geo.n_fft}, n_mels={n_mels}")
     flags = ((_lib.FLAG_NORMALIZE_WINDOW if normalize_window else 0) | (0 if remove_mean else _lib.FLAG_KEEP_MEAN)
              | (_lib.FLAG_TIME_MAJOR if time_major else 0))
     # 16-bit samples are widened in the kernels only if every entry's kernel family stages them

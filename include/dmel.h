@@ -145,7 +145,7 @@ DMEL_API size_t dmel_workspace_y_sum_offset(void);
  *               DMEL_FLAG_KEEP_MEAN: skip the per-clip mean removal of models.py:38 (what a
  *               direct caller of time_frequency.differentiable_spectrogram gets);
  *               DMEL_FLAG_TIME_MAJOR: emit [batch,1,T,rows] — the layout MelPANNsNet transposes to
- *               before Cnn6 (models.py:162) — tiled FFT path only (n_fft 128..4096)
+ *               before Cnn6 (models.py:162) — see dmel_time_major_supported
  *   y           [batch, 1, rows, T] fp32 contiguous, rows = n_mels or n_fft/2+1
  *   workspace   >= dmel_workspace_bytes(batch, n_fft); filled here (means, window,
  *               twiddles) and reusable by dmel_backward_f32 with prepared = 1      */
@@ -178,6 +178,9 @@ DMEL_API int dmel_forward_multi_f32(const void* x, int64_t batch, int64_t n_poin
  * backward a dot product (dmel_lambda_grad_f32): 1.0 instead of 1.5 FFTs per frame per training step, no
  * recomputation.  Tiled FFT path only (dmel_jvp_supported: n_fft 128..4096).                              */
 DMEL_API int dmel_jvp_supported(int32_t n_fft);
+/* 1 if DMEL_FLAG_TIME_MAJOR is served for this transform length: the tiled FFT kernels (128..4096, both modes) and the
+ * big-FFT path (8192 / 16384) with a mel bank (n_mels > 0) */
+DMEL_API int dmel_time_major_supported(int32_t n_fft, int32_t n_mels);
 /* 1 if 16-bit inputs (DMEL_FLAG_X_I16 / DMEL_FLAG_X_F16) are accepted for this transform length */
 DMEL_API int dmel_x16_supported(int32_t n_fft);
 DMEL_API int dmel_forward_jvp_f32(const void* x, int64_t batch, int64_t n_points, int64_t x_row_stride,

@@ -344,7 +344,8 @@ def test_drop_in_module_contract(cuda_device):
     assert net(x)[1].shape == (8, 1, 64, 101)
 
 
-@pytest.mark.parametrize("lam,M,sr,hop,N", [(46.667, 64, 8000, 80, 8000), (93.33, 128, 16000, 160, 16000), (257.25, 128, 44100, 441, 22050)])
+@pytest.mark.parametrize("lam,M,sr,hop,N", [(46.667, 64, 8000, 80, 8000), (93.33, 128, 16000, 160, 16000), (257.25, 128, 44100, 441, 22050),
+                                            (800.0, 64, 16000, 160, 16000)])      # last: n_fft 8192, the big-FFT path
 def test_time_major_layout_is_the_exact_transpose(cuda_device, lam, M, sr, hop, N):
     """MelPANNsNet transposes the layer output to (B,1,T,M) (models.py:162); the kernels can emit it."""
     dev = cuda_device
