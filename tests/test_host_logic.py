@@ -235,3 +235,44 @@ def test_missing_library_fails_loudly_instead_of_falling_back(monkeypatch, tmp_p
     layer = dm.MelSpectrogramLayer(torch.tensor(20.0), n_mels=8, n_points=800, sample_rate=8000, hop_length=80, optimized=True)
     with pytest.raises(dm.DmelError):
         layer(torch.randn(2, 800))              # CPU tensors are refused as well
+
+
+def test_folded_dft_with_3xtf32_split_is_fp32_accurate():
+    """The formulation of csrc/dmel_dftmm_kernels.cuh, restated in numpy: a frame folded around its centre
+    (e[j] = xw[j] + xw[L-j], o[j] = xw[j] - xw[L-j]) needs two real GEMMs with K = L/2, and operands split x = hi + lo
+    with hi = tf32(x) give fp32 accuracy from three tf32 products (the tensor core reads the upper 19 bits of lo)."""
+    def tf32_rna(a):                      # round to nearest, 10-bit mantissa (cvt.rna.tf32.f32)
+        u = a.astype(np.float32).view(np.uint32).astype(np.uint64)
+        u = (u + 0x1000) & 0xFFFFE000
+        return u.astype(np.uint32).view(np.float32)
+
+    def tf32_trunc(a):                    # what the MMA does to an fp32 operand
+        return (a.astype(np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    rng = np.random.default_rng(3)
+    for L in (128, 64, 100, 36):
+        H = L // 2
+        xw = (rng.standard_normal((40, L)) * np.exp(-0.5 * ((np.arange(L) - L / 2) / (L / 6)) ** 2)).astype(np.float32)
+        j = np.arange(H)
+        e = xw[:, :H].copy()
+        e[:, 1:] += xw[:, :H:-1][:, : H - 1]              # xw[L-j], j = 1..H-1
+        o = xw[:, :H].copy()
+        o[:, 1:] -= xw[:, :H:-1][:, : H - 1]
+        k = np.arange(H + 1)
+        ang = 2 * np.pi * np.outer(k, j) / L
+        cosm, sinm = np.cos(ang).astype(np.float32), (-np.sin(ang)).astype(np.float32)
+
+        def mm3(a, b):                    # A_hi B_hi + A_lo B_hi + A_hi B_lo, fp32 accumulation
+            ah, bh = tf32_rna(a), tf32_rna(b)
+            al, bl = tf32_trunc(a - ah), tf32_trunc(b - bh)
+            return (ah @ bh.T + al @ bh.T + ah @ bl.T).astype(np.float32)
+
+        re = mm3(e, cosm) + np.outer(xw[:, H], (-1.0) ** k).astype(np.float32)
+        im = mm3(o, sinm)
+        want = np.fft.rfft(xw.astype(np.float64), axis=1)
+        scale = np.abs(want).max()
+        assert np.abs(re - want.real).max() <= 2e-6 * scale, L
+        assert np.abs(im - want.imag).max() <= 2e-6 * scale, L
+        # a single tf32 pass (no split) is three orders of magnitude worse: the reason for the split
+        one = (tf32_rna(e) @ tf32_rna(cosm).T).astype(np.float32) + np.outer(xw[:, H], (-1.0) ** k).astype(np.float32)
+        assert np.abs(one - want.real).max() > 1e-4 * scale
