@@ -277,7 +277,9 @@ static int plan_launch(int64_t B, int64_t N, int n_fft, int hop, int rows, int c
                         const size_t sm2 = smem_of(1);
                         const int warps_cta = std::max(1, NG * gt / 32);
                         const bool cap96 = f2.ok ? (n_fft <= 512 && !bwd && !jvp) : (n_fft <= 512 && NG == 4 && !(bwd && need_dx));
-                        const int reg_cap = std::max(1, (cap96 ? 20 : 16) / warps_cta);
+                        int reg_cap = std::max(1, (cap96 ? 20 : 16) / warps_cta);
+                        // dmel2_bwd_kernel<1024,2,mel,dx> is compiled for 3 resident CTAs (160 registers, see its launch bounds)
+                        if (f2.ok && n_fft == 1024 && NG == 2 && bwd && need_dx && !spec_mode) reg_cap = 3;
                         auto ctas = [&](size_t b) { return std::min<int>(reg_cap, int(SMEM_MAX / (b + 1024))); };
                         lp->lookahead = 0;
                         if (!getenv("DMEL_NO_LOOKAHEAD") && sm2 <= SMEM_MAX && ctas(sm2) >= ctas(sm)) {

@@ -124,7 +124,7 @@ __host__ __device__ constexpr int min_ctas2(int NT, bool cap96) {
 // forward
 // ----------------------------------------------------------------------------
 template <int L, int NG, bool SPEC, bool JVP>
-__global__ void __launch_bounds__(NG * (L / 16), DMEL2_FWD_MINB(NG * (L / 16), L <= 512 && !JVP))
+__global__ void __launch_bounds__(NG * (L / 16), L == 4096 ? 1 : DMEL2_FWD_MINB(NG * (L / 16), L <= 512 && !JVP))
 dmel2_fwd_kernel(const void* __restrict__ x, float* __restrict__ y, float* __restrict__ dy, Geom g, MelDev mel,
                  const float* __restrict__ win_g, const float2* __restrict__ tw_g, const float* __restrict__ means,
                  WsHeader* hdr) {
@@ -459,7 +459,11 @@ dmel2_fwd_kernel(const void* __restrict__ x, float* __restrict__ y, float* __res
 #define DMEL2_BWD_MINB(NT) min_ctas2(NT, false)
 #endif
 template <int L, int NG, bool SPEC, bool NEED_DX>
-__global__ void __launch_bounds__(NG * (L / 16), DMEL2_BWD_MINB(NG * (L / 16)))
+// n_fft 1024 with dL/dx in mel mode: 57-75 KB of shared memory per CTA (two groups, their dx sub-spans, the dL/dy and y tiles)
+// limit the SM to 3 CTAs whatever the registers, so the kernel is compiled for 3 (up to 168 registers, it takes 160) instead
+// of 4 (128): backward -4 % on large_batch (profiles/r02/r03w_bwd1024_registers.log)
+// n_fft 4096 (256 threads, 1-2 CTAs per SM by shared memory): compiled without a register cap (-2.6 %, r03y)
+__global__ void __launch_bounds__(NG * (L / 16), (L == 1024 && NG == 2 && NEED_DX && !SPEC) ? 3 : (L == 4096 ? 1 : DMEL2_BWD_MINB(NG * (L / 16))))
 dmel2_bwd_kernel(const void* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy,
                  float* __restrict__ dx, Geom g, MelDev mel, const float* __restrict__ win_g,
                  const float2* __restrict__ tw_g, const float* __restrict__ means, WsHeader* hdr,
